@@ -1,0 +1,149 @@
+/* snfft_b200 -- C ABI of the B200-native S_n Fourier transform hot path.
+ *
+ * The reference (horacepan/SnFFT) is pure Python and has no FFI of its own; its boundary for
+ * this path is the set of Python call signatures in fft.py / yor.py.  This header is the C ABI
+ * that the Python mirror of those signatures (snfft_b200/fft.py, yor.py) binds with ctypes, and
+ * that a maintainer of the reference would bind the same way (INTEGRATION.md shows the stub).
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns an int status (0 = OK); the message of the last failure on the
+ *     calling thread is available from snfft_last_error(); nothing throws across the ABI;
+ *   - device buffers are owned by the caller; a plan owns its tables and is immutable after
+ *     creation, so concurrent calls on distinct streams are safe;
+ *   - all device work is asynchronous on the stream that is passed (a cudaStream_t as void*);
+ *   - there is no CPU fallback: calls that need a device fail with SNFFT_ERR_NO_DEVICE when the
+ *     plan was created host-only (device = -1).
+ *
+ * Data layout
+ *   functions on S_n : double[batch][n!]; order flag SNFFT_ORDER_LEX = rank of the permutation
+ *                      tuple in itertools.permutations order (reference perm2.py:214-233 `sn`),
+ *                      SNFFT_ORDER_COSET = coset-major order, flat = sum_k (i_k-1)(k-1)! for
+ *                      sigma = c^(n)_{i_n} ... c^(2)_{i_2}, c^(k)_i = (i i+1 ... k)
+ *                      (the order in which fft.py:96-98 visits the group);
+ *   spectrum         : double[batch][n!], "packed": for lambda in utils.partitions(n) order
+ *                      (reference utils.py:52-67) the row-major d_lambda x d_lambda matrix
+ *                      f_hat(lambda), rows/columns in the reference's tableau order
+ *                      (young_tableau.py:193-206).  sum_lambda d_lambda^2 = n!.
+ */
+#ifndef SNFFT_B200_H
+#define SNFFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNFFT_OK 0
+#define SNFFT_ERR_INVALID 1    /* bad argument */
+#define SNFFT_ERR_NO_DEVICE 2  /* host-only plan used for device work, or no CUDA device */
+#define SNFFT_ERR_CUDA 3       /* a CUDA runtime call failed; see snfft_last_error() */
+#define SNFFT_ERR_ALLOC 4
+
+#define SNFFT_ORDER_COSET 0
+#define SNFFT_ORDER_LEX 1
+
+#define SNFFT_MAX_N 12
+
+typedef struct snfft_plan snfft_plan;
+
+/* Version of this ABI (bumped when a signature changes). */
+int snfft_abi_version(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* snfft_last_error(void);
+
+/* Build the per-n tables: partitions in utils.partitions order, Young-lattice chains, tableau
+ * dimensions, packed offsets, the staged block programs of every level 2..n, and upload them to
+ * `device`.  device = -1 builds the host tables only (for inspection / CPU tests; such a plan
+ * cannot launch).  Replaces the tableau brute force of young_tableau.py:98-125 and the
+ * generator construction of yor.py:87-117 (K0 of SURVEY.md 7.1). */
+int snfft_plan_create(int n, int device, snfft_plan** out);
+int snfft_plan_destroy(snfft_plan* plan);
+
+int snfft_plan_n(const snfft_plan* plan);
+int snfft_plan_device(const snfft_plan* plan);
+/* number of irreps of S_k, 1 <= k <= n */
+int snfft_num_irreps(const snfft_plan* plan, int k);
+
+/* Irreps of S_k in utils.partitions(k) order (utils.py:52-67).  parts: int32[n_irreps][k]
+ * zero-padded rows; dims: int32[n_irreps] = number of standard tableaux (young_tableau.py:127);
+ * offsets: int64[n_irreps] = start of the row-major d x d block in the packed spectrum.
+ * Any output pointer may be NULL. */
+int snfft_layout(const snfft_plan* plan, int k, int32_t* parts, int32_t* dims, int64_t* offsets);
+
+/* branch_down of irrep `irrep` of S_k (young_tableau.py:62-81): indices into level k-1, in the
+ * reference's order, and the row/column offset of each block inside the d x d matrix.
+ * idx, off: int32[<= k]; *count receives the number of branches. */
+int snfft_branch_down(const snfft_plan* plan, int k, int irrep, int32_t* idx, int32_t* off,
+                      int32_t* count);
+
+/* rho_lambda((j j+1)) for irrep `irrep` of S_k, dense row-major double[d*d] on the HOST, read off
+ * the plan's chain-indexed coefficient tables (yor.py:87-117 `yor_trans`).  1 <= j < k. */
+int snfft_yor_trans(const snfft_plan* plan, int k, int irrep, int j, double* out_host);
+
+/* Forward transform f_hat(lambda) = sum_sigma f(sigma) rho_lambda(sigma) for every lambda |- n
+ * (fft.py:16-37 `ft_full`, :72-113 `fft`, :39-70 `fft2`).  f_dev: double[batch][n!] in `order`;
+ * fhat_dev: double[batch][n!] packed; work_dev: double[batch][n!] scratch (may alias neither).
+ * f_dev is preserved. */
+int snfft_forward(const snfft_plan* plan, const double* f_dev, double* fhat_dev, double* work_dev,
+                  int64_t batch, int order, void* stream);
+
+/* Inverse transform f(sigma) = (1/n!) sum_lambda d_lambda tr(rho_lambda(sigma)^T f_hat(lambda))
+ * (tile/par_inv_ft.py:27-45 evaluated for every sigma, by running the levels backwards).
+ * fhat_dev is preserved. */
+int snfft_inverse(const snfft_plan* plan, const double* fhat_dev, double* f_dev, double* work_dev,
+                  int64_t batch, int order, void* stream);
+
+/* One level of the recursion on its own (used by the sharded driver and by tests):
+ * in: double[groups][k][(k-1)!] = k packed S_{k-1} spectra per group; out: double[groups][k!]
+ * packed S_k spectra (fft.py:96-112).  inverse != 0 runs the level backwards. */
+int snfft_level(const snfft_plan* plan, int k, const double* in_dev, double* out_dev,
+                int64_t groups, int inverse, void* stream);
+
+/* Reorder between lexicographic and coset-major element order (the closure chain
+ * `f_i = lambda pi: f(cyc * pi)` of fft.py:97-98 as an index map).
+ * to_coset != 0: dst[b][t] = src[b][lex(t)]; else dst[b][lex(t)] = src[b][t]. */
+int snfft_reorder(const snfft_plan* plan, const double* src_dev, double* dst_dev, int64_t batch,
+                  int to_coset, void* stream);
+
+/* Host copy of the coset-major -> lexicographic index map, int64[n!]. */
+int snfft_coset_to_lex_host(const snfft_plan* plan, int64_t* out_host);
+
+/* rho_lambda(sigma) for `count` permutations (yor.py:52-85 `yor`): perms_dev int32[count][n]
+ * 1-based tuples, out_dev double[count][d*d] row-major, for irrep `irrep` of S_n. */
+int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
+              double* out_dev, void* stream);
+
+/* Direct sum f_hat = sum_sigma f(sigma) rho_lambda(sigma) for every lambda (fft.py:115-151
+ * `fourier_transform{,2}`) as one dense fp64 GEMM [batch, n!] x [n!, n!] on the DMMA pipe; the
+ * [n!, n!] matrix of all rho_lambda(sigma) is built on the device on first use.  n <= 7.
+ * f_dev: lexicographic order. */
+int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, int64_t batch,
+                     void* stream);
+
+/* Sizes of the plan's tables, for DESIGN.md / tests: bytes on the device, and multiply-adds per
+ * group element of level k (0 for k outside 2..n). */
+int64_t snfft_plan_device_bytes(const snfft_plan* plan);
+double snfft_level_macs_per_element(const snfft_plan* plan, int k);
+
+/* Number of kernels this library has launched on the calling process since load (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t snfft_launch_count(void);
+
+/* Host-side export of one panel program of level k (CPU tests interpret it in numpy to check the
+ * plan builder without a GPU).  panel = index of mu in partitions(k-1).  Buffers may be NULL to
+ * query sizes: *n_blocks = (k-1)*d_mu blocks in stage-major order; block_m[b] in 2..5;
+ * block_stage[b] in 1..k-1; block_slots int32[n_blocks][5]; block_coef double[n_blocks][25]
+ * (row-major m x m, out x in); dest int64[k*d_mu] offsets into the k! output of each slot;
+ * fscale double[k*d_mu]; iscale double[k*d_mu]. */
+int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_blocks,
+                       int32_t* block_m, int32_t* block_stage, int32_t* block_slots,
+                       double* block_coef, int64_t* dest, double* fscale, double* iscale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNFFT_B200_H */

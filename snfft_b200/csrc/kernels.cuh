@@ -1,0 +1,37 @@
+// Kernel launchers (definitions in kernels.cu).  All launches go on the given stream and bump the
+// library's launch counter.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_plan.hpp"
+
+namespace snfft {
+
+extern int64_t g_launch_count;
+
+// Streaming level kernel: global -> shared tile -> stages -> global.
+cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, size_t smem_bytes,
+                         const double* in, double* out, int64_t groups, bool inverse, int num_sms,
+                         cudaStream_t stream);
+
+// Fused low levels 2..k0 of `groups` independent S_{k0} blocks, entirely in shared memory.
+cudaError_t launch_fused(const FusedDev& F, const double* in, double* out, int64_t groups,
+                         bool inverse, int num_sms, cudaStream_t stream);
+
+// Element reorder lex <-> coset-major.  table may be null (index computed on the fly).
+cudaError_t launch_reorder(int n, const uint32_t* table, const double* src, double* dst,
+                           int64_t batch, bool to_coset, cudaStream_t stream);
+cudaError_t launch_build_lex_table(int n, uint32_t* table, cudaStream_t stream);
+
+// rho_lambda(sigma) for a list of permutations: rows tables are int32 partner[(n-1)][d] and
+// double diag[(n-1)][d] for the generators s_1..s_{n-1} of one irrep.
+cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
+                       const int32_t* perms, int64_t count, double* out, cudaStream_t stream);
+
+// C[M,N] = A[M,K] * B[K,N], fp64 row-major, on the DMMA pipe (mma.sync.m8n8k4.f64).
+cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K,
+                         cudaStream_t stream);
+
+cudaError_t prepare_kernels();  // opt in to large dynamic shared memory (once per process)
+
+}  // namespace snfft

@@ -1,0 +1,81 @@
+// Host-side plan of the S_n transform: Young lattice, tableau dimensions, packed layout and the
+// staged block programs of every level.  Pure C++ (no CUDA) so it can be built and inspected on a
+// CPU-only box.  Reference anchors: utils.py:52-67 (partitions order), young_tableau.py:62-81
+// (branch_down order), :193-206 (last-letter order), yor.py:87-117 (generator coefficients),
+// fft.py:96-112 (the level step that the block programs factorise).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace snfft {
+
+constexpr int kMaxN = 12;
+constexpr int kMaxBlock = 5;  // a shape with <= 11 cells has <= 4 corners -> blocks are <= 5x5
+
+struct Branch {
+  int idx;      // index of the neighbouring shape in its own level (partitions order)
+  int row, col; // the cell that is removed (down) / added (up), 0-based
+  int64_t off;  // down only: row/column offset of the mu-block inside the lambda matrix
+};
+
+struct ShapeInfo {
+  std::vector<int> rows;     // the partition
+  int64_t dim = 0;           // number of standard tableaux
+  int64_t off = 0;           // offset of the d x d block in the packed spectrum of its level
+  std::vector<Branch> down;  // young_tableau.py:62-81 order (rows top -> bottom)
+  std::vector<Branch> up;    // rows top -> bottom
+};
+
+struct LevelShapes {
+  std::vector<ShapeInfo> shapes;  // utils.partitions(k) order
+};
+
+// One small dense block of a stage: out[a] = sum_b coef[a][b] * in[b], in place on `slot`.
+struct alignas(16) Block {
+  uint16_t slot[kMaxBlock];
+  uint16_t m;
+  uint32_t coef;  // offset (in doubles) of the row-major m x m matrix in the level's pool
+};
+static_assert(sizeof(Block) == 16, "Block must be 16 bytes");
+
+// Program of one column block mu |- k-1 of level k: k*d rows ("slots"), k-1 stages of d blocks.
+struct PanelProgram {
+  int k = 0, mu = 0;
+  int d = 0;                       // d_mu
+  int64_t in_off = 0;              // packed offset of mu in a level-(k-1) spectrum
+  std::vector<Block> blocks;       // stage-major: stage s (1..k-1) is blocks[(s-1)*d, s*d)
+  std::vector<uint32_t> dest;      // slot -> offset in the k! output (start of a run of d)
+  std::vector<double> fscale;      // slot -> scale applied when writing the forward output
+  std::vector<double> iscale;      // slot -> scale applied when loading the inverse input
+  std::vector<uint32_t> rowbase;   // slot -> offset in the k! input (start of a run of d)
+};
+
+struct LevelProgram {
+  int k = 0;
+  std::vector<PanelProgram> panels;  // one per mu in partitions(k-1) order
+  std::vector<double> coef;          // deduplicated coefficient matrices
+  double macs = 0;                   // multiply-adds per group of k! elements
+};
+
+struct HostPlan {
+  int n = 0;
+  std::vector<LevelShapes> levels;     // levels[0..n]; levels[0] holds the empty shape
+  std::vector<LevelProgram> programs;  // programs[k], k = 2..n (0,1 unused)
+  int64_t fact[kMaxN + 2];
+};
+
+// Throws std::runtime_error on invalid n.
+void build_host_plan(int n, HostPlan& plan);
+
+// Dense rho_lambda((j j+1)) for shape `irrep` of level k (row-major d*d), from lattice chains.
+void yor_trans_dense(const HostPlan& plan, int k, int irrep, int j, double* out);
+
+// Per-row description of rho_lambda((j j+1)): partner row (or -1) and the diagonal coefficient.
+void yor_trans_rows(const HostPlan& plan, int k, int irrep, int j, std::vector<int32_t>& partner,
+                    std::vector<double>& diag);
+
+// coset-major flat index -> lexicographic rank (host).
+int64_t coset_to_lex(int n, int64_t flat, const int64_t* fact);
+
+}  // namespace snfft
