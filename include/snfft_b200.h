@@ -119,7 +119,7 @@ int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64
 
 /* Direct sum f_hat = sum_sigma f(sigma) rho_lambda(sigma) for every lambda (fft.py:115-151
  * `fourier_transform{,2}`) as one dense fp64 GEMM [batch, n!] x [n!, n!] on the DMMA pipe; the
- * [n!, n!] matrix of all rho_lambda(sigma) is built on the device on first use.  n <= 7.
+ * [n!, n!] matrix of all rho_lambda(sigma) is built on the device on first use.  n <= 8 (13 GB at n = 8).
  * f_dev: lexicographic order. */
 int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, int64_t batch,
                      void* stream);

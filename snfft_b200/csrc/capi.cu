@@ -494,7 +494,7 @@ int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, in
   return guarded([&] {
     require_device(plan);
     const int n = plan->host.n;
-    if (n > 7) throw InvalidArg("snfft_dft_direct supports n <= 7 (the [n!, n!] matrix must fit)");
+    if (n > 8) throw InvalidArg("snfft_dft_direct supports n <= 8 (the [n!, n!] matrix is 13 GB at n = 8)");
     if (batch < 0) throw InvalidArg("batch < 0");
     if (batch == 0) return;
     if (!f_dev || !fhat_dev || f_dev == fhat_dev) throw InvalidArg("bad buffers");

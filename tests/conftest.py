@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a B200 (run with -m gpu on the GPU box)')
+
+
+@pytest.fixture(scope='session')
+def golden_small():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'reference_small.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_s8():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'reference_s8.npz'))
+
+
+def rel_fro(a, b):
+    """Relative Frobenius error of a against b (b is the reference)."""
+    import numpy as np
+    denom = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (denom if denom > 0 else 1.0))

@@ -1,0 +1,86 @@
+"""The reference-shaped Python entry points (snfft_b200.fft / yor) on the GPU, written the way
+the reference's own test.py exercises them."""
+import math
+
+import numpy as np
+import pytest
+
+import snfft_oracle as O
+from conftest import rel_fro
+from snfft_b200 import fft as sfft
+from snfft_b200 import perm2
+from snfft_b200.perm import Perm
+from snfft_b200.perm2 import Perm2
+from snfft_b200.utils import partitions
+from snfft_b200.yor import yor, yor_trans
+from snfft_b200.young_tableau import FerrersDiagram
+
+pytestmark = pytest.mark.gpu
+
+
+def test_yor_known_answers():
+    # test.py:66-74
+    ferr = FerrersDiagram((3, 1))
+    p12 = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    p23 = np.array([[0.5, np.sqrt(3) / 2., 0], [np.sqrt(3) / 2., -0.5, 0], [0, 0, 1]])
+    p34 = np.array([[1, 0, 0], [0, 1. / 3., np.sqrt(8) / 3], [0, np.sqrt(8) / 3, -1. / 3.]])
+    assert np.allclose(p12, yor(ferr, Perm2({1: 2, 2: 1}, 4)))
+    assert np.allclose(p23, yor(ferr, Perm2({2: 3, 3: 2}, 4)))
+    assert np.allclose(p34, yor(ferr, Perm2({3: 4, 4: 3}, 4)))
+    assert np.allclose(p34, yor_trans(ferr, (3, 4)))
+    assert np.allclose(yor(ferr, Perm2.eye(4)), np.eye(3))
+    assert np.allclose(yor(ferr, Perm([(3, 4)])), p34)          # short tuple is padded
+
+
+def test_fft_reference_test(golden_small):
+    # test.py:76-85
+    f = lambda p: 1 if p[1] == 2 else 1.5   # noqa: E731
+    ref_fft = O.unpack(golden_small['testpy_fft_6'], 6)
+    # f depends on sigma(1) only, so most irreps are exactly zero in exact arithmetic: measure the
+    # error against the norm of the whole spectrum there
+    scale = np.linalg.norm(golden_small['testpy_fft_6'])
+    for partition in partitions(6):
+        ferrers = FerrersDiagram(partition)
+        fft_res = sfft.fft(f, ferrers)
+        ft = sfft.fourier_transform(f, ferrers)
+        ft2 = sfft.fourier_transform2(f, ferrers)
+        assert np.allclose(ft, ft2)
+        assert np.allclose(fft_res, ft)
+        assert fft_res.shape == (ferrers.n_tabs(),) * 2 and fft_res.dtype == np.float64
+        assert np.linalg.norm(fft_res - ref_fft[partition]) < 1e-10 * scale
+        assert np.linalg.norm(sfft.fft2(f, ferrers) - ref_fft[partition]) < 1e-10 * scale   # raises in the reference
+
+
+def test_ft_full_all_algos(golden_small):
+    n = 5
+    values = np.random.default_rng(5).standard_normal(120)
+    lut = {p.tup_rep: values[i] for i, p in enumerate(perm2.sn(n))}
+
+    def f(p):
+        t = tuple(p.tup_rep)
+        return lut[t + tuple(range(len(t) + 1, n + 1))]
+    ref = O.unpack(golden_small['direct_5'], 5)
+    for algo in ('fft', 'ft1', 'ft2'):
+        res = sfft.ft_full(f, n, algo)
+        assert [k.partition for k in res] == partitions(n)
+        for k, v in res.items():
+            assert rel_fro(v, ref[k.partition]) < 1e-10
+    back = sfft.ift_full(sfft.ft_full(f, n), n)
+    assert rel_fro(back, values) < 1e-10
+
+
+def test_dense_api_round_trip():
+    values = np.random.default_rng(1).standard_normal((4, math.factorial(6)))
+    spec = sfft.forward(values)
+    assert list(spec) == partitions(6)
+    assert rel_fro(sfft.inverse(spec, 6), values) < 1e-10
+
+
+def test_yor_random_homomorphism_n7():
+    # test.py:87-101 through the public API
+    rng = np.random.default_rng(3)
+    for p in partitions(7)[::3]:
+        fd = FerrersDiagram(p)
+        g = Perm2.from_tup(tuple(int(x) + 1 for x in rng.permutation(7)))
+        h = Perm2.from_tup(tuple(int(x) + 1 for x in rng.permutation(7)))
+        assert np.allclose(yor(fd, g) @ yor(fd, h), yor(fd, g * h))

@@ -1,0 +1,157 @@
+"""The C-ABI library on a CPU-only box: it loads, exports every symbol the header declares, and
+its host-side plan builder (no device) reproduces the reference's tables and, when its block
+programs are interpreted in numpy, the reference's level step.  No compute call is made on a
+device here."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import snfft_oracle as O
+from conftest import rel_fro
+from snfft_b200 import Plan
+from snfft_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'snfft_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(snfft_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    for name in declared:
+        assert hasattr(N.lib, name)
+    assert N.lib.snfft_abi_version() == 1
+
+
+def test_plan_create_errors():
+    h = C.c_void_p()
+    assert N.lib.snfft_plan_create(0, -1, C.byref(h)) == 1
+    assert N.lib.snfft_plan_create(13, -1, C.byref(h)) == 1
+    assert b'1..12' in N.lib.snfft_last_error()
+    assert N.lib.snfft_plan_create(4, -1, None) == 1
+    with pytest.raises(N.SnfftError):
+        Plan(4, 99)                                  # no such device: fails loudly, no fallback
+
+
+def test_host_only_plan_refuses_device_work():
+    plan = Plan(4, -1)
+    buf = np.zeros(24)
+    rc = N.lib.snfft_forward(plan._h, N.ptr(buf), N.ptr(buf.copy()), N.ptr(buf.copy()), 1, 1, None)
+    assert rc == 2 and b'no CPU fallback' in N.lib.snfft_last_error()
+    assert N.lib.snfft_inverse(plan._h, N.ptr(buf), N.ptr(buf.copy()), N.ptr(buf.copy()), 1, 1, None) == 2
+    assert N.lib.snfft_level(plan._h, 3, N.ptr(buf), N.ptr(buf.copy()), 4, 0, None) == 2
+
+
+@pytest.mark.parametrize('n', range(1, 11))
+def test_layout_matches_oracle(n):
+    plan = Plan(n, -1)
+    parts, dims, offs = plan.layout()
+    assert parts == O.partitions(n)
+    assert sum(d * d for d in dims) == math.factorial(n)
+    if n <= 8:
+        o_offs, o_dims = O.packed_layout(n)
+        assert dims == [o_dims[p] for p in parts] and offs == [o_offs[p] for p in parts]
+    for i, p in enumerate(parts):
+        idx, off = plan.branch_down(n, i)
+        sub = plan.layout(n - 1)[0] if n > 1 else []
+        assert [sub[j] for j in idx] == O.branch_down(p)
+        assert off == list(np.cumsum([0] + [plan.layout(n - 1)[1][j] for j in idx])[:-1]) or n == 1
+
+
+def test_hook_length_dimensions_n12():
+    plan = Plan(12, -1)
+    parts, dims, _ = plan.layout()
+    assert len(parts) == 77 and max(dims) == 7700 and sum(dims) == 140152
+
+    def hook(p):
+        conj = [sum(1 for r in p if r > c) for c in range(p[0])]
+        prod = 1
+        for r, length in enumerate(p):
+            for c in range(length):
+                prod *= (length - c - 1) + (conj[c] - r - 1) + 1
+        return math.factorial(sum(p)) // prod
+    assert dims == [hook(p) for p in parts]
+
+
+@pytest.mark.parametrize('n', range(2, 8))
+def test_yor_trans_tables_bit_exact(golden_small, n):
+    plan = Plan(n, -1)
+    for i, p in enumerate(plan.layout()[0]):
+        for k in range(1, n):
+            ref = golden_small['yortrans_{}_{}'.format('_'.join(map(str, p)), k)]
+            assert np.array_equal(plan.yor_trans(n, i, k), ref)
+    h = plan._h
+    assert N.lib.snfft_yor_trans(h, n, 0, n, N.ptr(np.zeros(1))) == 1     # j out of range
+
+
+def interpret_level(plan, k, x, inverse=False):
+    """Run the exported block programs of level k in numpy: [k, (k-1)!] <-> [k!]."""
+    parts, dims, offs = plan.layout(k - 1)
+    kf = math.factorial(k)
+    out = np.zeros(kf) if not inverse else np.zeros((k, kf // k))
+    for pi, (d, o) in enumerate(zip(dims, offs)):
+        prog = plan.export_panel(k, pi)
+        assert prog['d'] == d and len(prog['m']) == (k - 1) * d
+        assert sorted(set(prog['slots'][prog['slots'] >= 0])) == list(range(k * d)) or k == 2
+        stages = [np.nonzero(prog['stage'] == s)[0] for s in range(1, k)]
+        if not inverse:
+            buf = np.concatenate([x[i, o:o + d * d].reshape(d, d) for i in range(k)], axis=0)
+        else:
+            buf = np.stack([prog['iscale'][s] * x[prog['dest'][s]:prog['dest'][s] + d] for s in range(k * d)])
+        for blocks in (reversed(stages) if inverse else stages):
+            for b in blocks:
+                m = prog['m'][b]
+                sl = prog['slots'][b, :m]
+                cm = prog['coef'][b, :m * m].reshape(m, m)
+                buf[sl] = (cm.T if inverse else cm) @ buf[sl]
+        if not inverse:
+            for s in range(k * d):
+                out[prog['dest'][s]:prog['dest'][s] + d] = prog['fscale'][s] * buf[s]
+        else:
+            for i in range(k):
+                out[i, o:o + d * d] = buf[i * d:(i + 1) * d].reshape(-1)
+    return out
+
+
+@pytest.mark.parametrize('n', range(2, 8))
+def test_block_programs_reproduce_the_level_step(n):
+    plan = Plan(n, -1)
+    f = np.random.default_rng(100 + n).standard_normal(math.factorial(n))
+    gather = O._coset_gather(n)
+    subs = np.stack([O.pack(O.fft_all(f[gather[i]]), n - 1) for i in range(n)])
+    ref = O.pack(O.fft_all(f), n)
+    got = interpret_level(plan, n, subs)
+    for p, a in O.unpack(got, n).items():
+        assert rel_fro(a, O.unpack(ref, n)[p]) < 1e-13, p
+    back = interpret_level(plan, n, ref, inverse=True)
+    assert np.abs(back - subs).max() < 1e-12
+
+
+def test_whole_transform_from_block_programs_n6():
+    n = 6
+    plan = Plan(n, -1)
+    f = np.random.default_rng(6).standard_normal(720)
+    x = f[plan.coset_to_lex()]
+    for k in range(2, n + 1):
+        groups = x.reshape(-1, k, math.factorial(k - 1))
+        x = np.concatenate([interpret_level(plan, k, g) for g in groups])
+    assert rel_fro(x, O.pack(O.fft_all(f), n)) < 1e-13
+
+
+@pytest.mark.parametrize('n', range(1, 9))
+def test_coset_to_lex_map(n):
+    assert np.array_equal(Plan(n, -1).coset_to_lex(), O.coset_major_to_lex(n))
+
+
+def test_operation_counts():
+    plan = Plan(12, -1)
+    macs = [plan.macs_per_element(k) for k in range(2, 13)]
+    assert abs(macs[0] - 2.0) < 1e-12 and all(b > a for a, b in zip(macs, macs[1:]))
+    assert sum(macs) < 0.75 * 12 * 11          # below Maslen's (3/4) n (n-1) bound
+    assert plan.macs_per_element(1) == 0.0 and plan.macs_per_element(13) == 0.0
