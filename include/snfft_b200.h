@@ -133,6 +133,14 @@ double snfft_level_macs_per_element(const snfft_plan* plan, int k);
  * gpu_launches claim is read from here). */
 int64_t snfft_launch_count(void);
 
+/* Per-kernel timing for bench.py: when enabled, every launch of this library is bracketed by CUDA
+ * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[8] and
+ * launches_by_kind[8] (0 fused forward, 1 fused inverse, 2 level forward, 3 level inverse,
+ * 4 reorder, 5 yor, 6 dgemm, 7 other) and resets the totals. */
+#define SNFFT_NUM_KERNEL_KINDS 8
+int snfft_timing_enable(int on);
+int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind);
+
 /* Host-side export of one panel program of level k (CPU tests interpret it in numpy to check the
  * plan builder without a GPU).  panel = index of mu in partitions(k-1).  Buffers may be NULL to
  * query sizes: *n_blocks = (k-1)*d_mu blocks in stage-major order; block_m[b] in 2..5;

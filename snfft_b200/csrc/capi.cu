@@ -546,6 +546,18 @@ double snfft_level_macs_per_element(const snfft_plan* plan, int k) {
 
 int64_t snfft_launch_count(void) { return g_launch_count; }
 
+int snfft_timing_enable(int on) {
+  timing_enable(on != 0);
+  return SNFFT_OK;
+}
+
+int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind) {
+  return guarded([&] {
+    if (!ms_by_kind || !launches_by_kind) throw InvalidArg("null argument");
+    timing_read(ms_by_kind, launches_by_kind);
+  });
+}
+
 int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_blocks,
                        int32_t* block_m, int32_t* block_stage, int32_t* block_slots,
                        double* block_coef, int64_t* dest, double* fscale, double* iscale) {

@@ -10,9 +10,79 @@
 // against HBM (16 B per element per pass) and shared-memory bandwidth.
 #include "kernels.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace snfft {
 
 int64_t g_launch_count = 0;
+
+namespace {
+struct TimedLaunch {
+  int kind;
+  cudaEvent_t start, stop;
+};
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+std::vector<cudaEvent_t> g_event_pool;
+std::mutex g_timing_mu;
+
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// brackets one launch with events when timing is on
+struct LaunchScope {
+  cudaStream_t stream;
+  bool on;
+  TimedLaunch t;
+  LaunchScope(int kind, cudaStream_t s) : stream(s), on(g_timing) {
+    ++g_launch_count;
+    if (on) {
+      std::lock_guard<std::mutex> lock(g_timing_mu);
+      t.kind = kind;
+      t.start = get_event();
+      t.stop = get_event();
+      cudaEventRecord(t.start, stream);
+    }
+  }
+  ~LaunchScope() {
+    if (on) {
+      cudaEventRecord(t.stop, stream);
+      std::lock_guard<std::mutex> lock(g_timing_mu);
+      g_timed.push_back(t);
+    }
+  }
+};
+}  // namespace
+
+void timing_enable(bool on) { g_timing = on; }
+
+void timing_read(double* ms_by_kind, int64_t* launches_by_kind) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  for (int i = 0; i < kNumKinds; ++i) {
+    ms_by_kind[i] = 0.0;
+    launches_by_kind[i] = 0;
+  }
+  for (TimedLaunch& t : g_timed) {
+    cudaEventSynchronize(t.stop);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess) {
+      ms_by_kind[t.kind] += ms;
+      launches_by_kind[t.kind] += 1;
+    }
+    g_event_pool.push_back(t.start);
+    g_event_pool.push_back(t.stop);
+  }
+  g_timed.clear();
+}
 
 namespace {
 
@@ -404,11 +474,11 @@ cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, s
   if (y < 1) y = 1;
   if (y > 65535) y = 65535;
   dim3 grid((unsigned)ntiles, (unsigned)y);
+  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
   if (inverse)
     level_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(L, tiles_dev, in, out, groups);
   else
     level_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(L, tiles_dev, in, out, groups);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 
@@ -421,11 +491,11 @@ cudaError_t launch_fused(const FusedDev& F, const double* in, double* out, int64
   if (per_sm > 8) per_sm = 8;
   int64_t grid = (int64_t)num_sms * per_sm;
   if (grid > groups) grid = groups;
+  LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
   if (inverse)
     fused_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
   else
     fused_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 
@@ -433,8 +503,8 @@ cudaError_t launch_build_lex_table(int n, uint32_t* table, cudaStream_t stream) 
   const Facts F = make_facts();
   const int64_t total = F.f[n];
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  LaunchScope scope(kKindOther, stream);
   build_lex_table_kernel<<<blocks, 256, 0, stream>>>(n, F, table);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 
@@ -447,19 +517,19 @@ cudaError_t launch_reorder(int n, const uint32_t* table, const double* src, doub
   if (bx > 2048) bx = 2048;
   int64_t by = batch < 64 ? batch : 64;
   dim3 grid((unsigned)bx, (unsigned)by);
+  LaunchScope scope(kKindReorder, stream);
   if (to_coset)
     reorder_kernel<true><<<grid, 256, 0, stream>>>(n, F, table, src, dst, batch);
   else
     reorder_kernel<false><<<grid, 256, 0, stream>>>(n, F, table, src, dst, batch);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 
 cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
                        const int32_t* perms, int64_t count, double* out, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
+  LaunchScope scope(kKindYor, stream);
   yor_kernel<<<(unsigned)count, kThreads, 0, stream>>>(n, d, partner, diag, perms, out);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 
@@ -467,8 +537,8 @@ cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int
                          cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
+  LaunchScope scope(kKindDgemm, stream);
   dgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K);
-  ++g_launch_count;
   return cudaGetLastError();
 }
 

@@ -9,6 +9,13 @@ namespace snfft {
 
 extern int64_t g_launch_count;
 
+// Optional per-launch timing (bench.py): when enabled every launch is bracketed by CUDA events on
+// its own stream; timing_read() synchronises the recorded events and returns the totals per kind.
+enum KernelKind { kKindFusedFwd = 0, kKindFusedInv, kKindLevelFwd, kKindLevelInv, kKindReorder,
+                  kKindYor, kKindDgemm, kKindOther, kNumKinds };
+void timing_enable(bool on);
+void timing_read(double* ms_by_kind, int64_t* launches_by_kind);  // also resets the totals
+
 // Streaming level kernel: global -> shared tile -> stages -> global.
 cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, size_t smem_bytes,
                          const double* in, double* out, int64_t groups, bool inverse, int num_sms,

@@ -223,3 +223,18 @@ def get_plan(n: int, device: int = 0) -> Plan:
 
 def launch_count() -> int:
     return int(N.lib.snfft_launch_count())
+
+
+KERNEL_KINDS = ("fused_fwd", "fused_inv", "level_fwd", "level_inv", "reorder", "yor", "dgemm", "other")
+
+
+def timing_enable(on: bool) -> None:
+    N.check(N.lib.snfft_timing_enable(int(bool(on))))
+
+
+def timing_read():
+    """{kind: (total ms, launches)} since the last read (synchronises the recorded events)."""
+    ms = np.zeros(len(KERNEL_KINDS), dtype=np.float64)
+    cnt = np.zeros(len(KERNEL_KINDS), dtype=np.int64)
+    N.check(N.lib.snfft_timing_read(N.ptr(ms), N.ptr(cnt)))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
