@@ -144,12 +144,15 @@ int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind);
 /* Host-side export of one panel program of level k (CPU tests interpret it in numpy to check the
  * plan builder without a GPU).  panel = index of mu in partitions(k-1).  Buffers may be NULL to
  * query sizes: *n_blocks = (k-1)*d_mu blocks in stage-major order; block_m[b] in 2..5;
- * block_stage[b] in 1..k-1; block_slots int32[n_blocks][5]; block_coef double[n_blocks][25]
- * (row-major m x m, out x in); dest int64[k*d_mu] offsets into the k! output of each slot;
- * fscale double[k*d_mu]; iscale double[k*d_mu]. */
+ * block_stage[b] in 1..k-1; block_slots int32[n_blocks][5] (-1 padded); block_final[b] = bit mask
+ * of the outputs that are finished rows; coef_fwd / coef_inv double[n_blocks][25] (row-major
+ * m x m: forward out x in, inverse in x out, all scalings folded in); dest int64[k*d_mu] = offset
+ * of each slot's finished row in the k! output; rowbase int64[k*d_mu] = offset of each slot's
+ * input row in the k! input. */
 int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_blocks,
                        int32_t* block_m, int32_t* block_stage, int32_t* block_slots,
-                       double* block_coef, int64_t* dest, double* fscale, double* iscale);
+                       int32_t* block_final, double* coef_fwd, double* coef_inv, int64_t* dest,
+                       int64_t* rowbase);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,7 @@ SIGNATURES = {
     "snfft_launch_count": (C.c_int64, []),
     "snfft_timing_enable": (C.c_int, [C.c_int]),
     "snfft_timing_read": (C.c_int, [_p, _p]),
-    "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -15,7 +15,9 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libsnfft_b200.so")
 SOURCES = ["plan.cpp", "kernels.cu", "capi.cu"]
-HEADERS = ["plan.hpp", "device_plan.hpp", "kernels.cuh", os.path.join("..", "..", "include", "snfft_b200.h")]
+HEADERS = ["plan.hpp", "device_plan.hpp", "kernels.cuh", "gen_programs.cpp",
+           os.path.join("..", "..", "include", "snfft_b200.h")]
+GENERATED = os.path.join(CSRC, "gen_small.cuh")
 
 
 def nvcc_path() -> str:
@@ -33,10 +35,28 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+def generate() -> str:
+    """Regenerate csrc/gen_small.cuh (straight-line register programs of levels 2..6) from the
+    plan builder: g++ gen_programs.cpp plan.cpp && ./gen_programs gen_small.cuh."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "gen_programs")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(CSRC, "gen_programs.cpp"),
+                        os.path.join(CSRC, "plan.cpp")], check=True)
+        fresh = os.path.join(tmp, "gen_small.cuh")
+        subprocess.run([exe, fresh], check=True)
+        new = open(fresh).read()
+    if not os.path.exists(GENERATED) or open(GENERATED).read() != new:
+        with open(GENERATED, "w") as fh:
+            fh.write(new)
+    return GENERATED
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
+    generate()
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-o", OUT]
     if verbose:

@@ -136,7 +136,6 @@ void upload_level(snfft_plan* plan, int k) {
   std::vector<PanelDev> panels;
   std::vector<Block> blocks;
   std::vector<uint32_t> dest, rowbase;
-  std::vector<double> fscale, iscale;
   int32_t item_off = 0;
   for (const PanelProgram& P : prog.panels) {
     PanelDev pd;
@@ -151,8 +150,6 @@ void upload_level(snfft_plan* plan, int k) {
     blocks.insert(blocks.end(), P.blocks.begin(), P.blocks.end());
     dest.insert(dest.end(), P.dest.begin(), P.dest.end());
     rowbase.insert(rowbase.end(), P.rowbase.begin(), P.rowbase.end());
-    fscale.insert(fscale.end(), P.fscale.begin(), P.fscale.end());
-    iscale.insert(iscale.end(), P.iscale.begin(), P.iscale.end());
   }
   LevelDev& L = plan->level_dev[k];
   L.k = k;
@@ -163,34 +160,17 @@ void upload_level(snfft_plan* plan, int k) {
   L.blocks = plan->upload(blocks);
   L.coef = plan->upload(prog.coef);
   L.dest = plan->upload(dest);
-  L.fscale = plan->upload(fscale);
-  L.iscale = plan->upload(iscale);
   L.rowbase = plan->upload(rowbase);
   L.item_tab = nullptr;
-  L.copy_dest = nullptr;
-  L.copy_fscale = nullptr;
-  L.copy_iscale = nullptr;
-  if (k <= kFusedMax) {
-    const int64_t km1 = plan->host.fact[k - 1], kf = plan->host.fact[k];
-    std::vector<uint32_t> item_tab(km1), copy_dest(kf);
-    std::vector<double> copy_f(kf), copy_i(kf);
+  if (k == kFusedMax) {
+    std::vector<uint32_t> item_tab(plan->host.fact[k - 1]);
     for (size_t p = 0; p < prog.panels.size(); ++p) {
       const PanelProgram& P = prog.panels[p];
       for (int q = 0; q < P.d; ++q)
         for (int c = 0; c < P.d; ++c)
           item_tab[panels[p].item_off + q * P.d + c] = ((uint32_t)p << 24) | ((uint32_t)q << 12) | (uint32_t)c;
-      for (int s = 0; s < P.k * P.d; ++s)
-        for (int c = 0; c < P.d; ++c) {
-          const int64_t r = (int64_t)P.rowbase[s] + c;
-          copy_dest[r] = P.dest[s] + c;
-          copy_f[r] = P.fscale[s];
-          copy_i[r] = P.iscale[s];
-        }
     }
     L.item_tab = plan->upload(item_tab);
-    L.copy_dest = plan->upload(copy_dest);
-    L.copy_fscale = plan->upload(copy_f);
-    L.copy_iscale = plan->upload(copy_i);
   }
   std::vector<Tile> tiles;
   plan_tiles(prog, tiles, plan->level_smem[k]);
@@ -280,7 +260,8 @@ int snfft_plan_create(int n, int device, snfft_plan** out) {
     plan = new snfft_plan();
     build_host_plan(n, plan->host);
     plan->device = device;
-    plan->fused.k0 = std::min(n, kFusedMax);
+    // levels 2..k0 run in the fused kernel (k0 = min(n, 7)); for n <= 3 nothing is fused (k0 = 1)
+    plan->fused.k0 = n >= 4 ? std::min(n, kFusedMax) : 1;
     plan->fused.k0fact = (int32_t)plan->host.fact[plan->fused.k0];
     if (device >= 0) {
       int count = 0;
@@ -293,7 +274,7 @@ int snfft_plan_create(int n, int device, snfft_plan** out) {
       plan->num_sms = prop.multiProcessorCount;
       CUDA_OK(prepare_kernels());
       for (int k = 2; k <= n; ++k) upload_level(plan, k);
-      for (int k = 2; k <= plan->fused.k0; ++k) plan->fused.level[k] = plan->level_dev[k];
+      for (int k = 2; k <= std::min(n, kFusedMax); ++k) plan->fused.level[k] = plan->level_dev[k];
       if (n <= 10) {
         plan->lex_table = (uint32_t*)plan->alloc((size_t)plan->host.fact[n] * sizeof(uint32_t));
         CUDA_OK(launch_build_lex_table(n, plan->lex_table, 0));
@@ -386,17 +367,30 @@ int snfft_forward(const snfft_plan* plan, const double* f_dev, double* fhat_dev,
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n = plan->host.n, k0 = plan->fused.k0;
     const int64_t nf = plan->host.fact[n];
-    const double* src = f_dev;
-    if (order == SNFFT_ORDER_LEX && n >= 2) {
-      CUDA_OK(launch_reorder(n, plan->lex_table, f_dev, work_dev, batch, true, stream));
-      src = work_dev;
+    if (n == 1) {
+      CUDA_OK(cudaMemcpyAsync(fhat_dev, f_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      return;
     }
-    const int passes = n - k0;  // streaming level passes after the fused kernel
-    double* cur = (passes % 2 == 0) ? fhat_dev : work_dev;
-    CUDA_OK(launch_fused(plan->fused, src, cur, batch * (nf / plan->fused.k0fact), false,
-                         plan->num_sms, stream));
+    // passes: [fused 2..k0 if n >= 4] then one streaming pass per level k0+1..n.  Outputs alternate
+    // between work and fhat so that the last one lands in fhat; f is never written.
+    const int npasses = (k0 >= 4 ? 1 : 0) + (n - k0);
+    auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? fhat_dev : work_dev; };
+    const double* cur = f_dev;
+    if (order == SNFFT_ORDER_LEX) {
+      // reorder into the buffer the first pass does not write (a level pass cannot run in place)
+      double* tmp = out_of(0) == fhat_dev ? work_dev : fhat_dev;
+      CUDA_OK(launch_reorder(n, plan->lex_table, f_dev, tmp, batch, true, stream));
+      cur = tmp;
+    }
+    int pass = 0;
+    if (k0 >= 4) {
+      double* nxt = out_of(pass++);
+      CUDA_OK(launch_fused(plan->fused, cur, nxt, batch * (nf / plan->fused.k0fact), false,
+                           plan->num_sms, stream));
+      cur = nxt;
+    }
     for (int k = k0 + 1; k <= n; ++k) {
-      double* nxt = (cur == fhat_dev) ? work_dev : fhat_dev;
+      double* nxt = out_of(pass++);
       run_level(plan, k, cur, nxt, batch * (nf / plan->host.fact[k]), false, stream);
       cur = nxt;
     }
@@ -417,19 +411,31 @@ int snfft_inverse(const snfft_plan* plan, const double* fhat_dev, double* f_dev,
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n = plan->host.n, k0 = plan->fused.k0;
     const int64_t nf = plan->host.fact[n];
-    const bool lex = order == SNFFT_ORDER_LEX && n >= 2;
+    if (n == 1) {
+      CUDA_OK(cudaMemcpyAsync(f_dev, fhat_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      return;
+    }
+    const bool lex = order == SNFFT_ORDER_LEX;
+    // passes: streaming levels n..k0+1, then the fused kernel (levels k0..2).  The last pass writes
+    // `target` (work when a reorder to lexicographic order follows, else f); earlier outputs
+    // alternate; fhat is never written.
+    const int npasses = (k0 >= 4 ? 1 : 0) + (n - k0);
+    double* target = lex ? work_dev : f_dev;
+    double* other = lex ? f_dev : work_dev;
+    auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? target : other; };
     const double* cur = fhat_dev;
-    double* bufs[2] = {work_dev, f_dev};
-    int which = 0;
+    int pass = 0;
     for (int k = n; k > k0; --k) {
-      double* nxt = bufs[which];
-      which ^= 1;
+      double* nxt = out_of(pass++);
       run_level(plan, k, cur, nxt, batch * (nf / plan->host.fact[k]), true, stream);
       cur = nxt;
     }
-    double* target = lex ? work_dev : f_dev;
-    CUDA_OK(launch_fused(plan->fused, cur, target, batch * (nf / plan->fused.k0fact), true,
-                         plan->num_sms, stream));
+    if (k0 >= 4) {
+      double* nxt = out_of(pass++);
+      CUDA_OK(launch_fused(plan->fused, cur, nxt, batch * (nf / plan->fused.k0fact), true,
+                           plan->num_sms, stream));
+      cur = nxt;
+    }
     if (lex) CUDA_OK(launch_reorder(n, plan->lex_table, work_dev, f_dev, batch, false, stream));
   });
 }
@@ -560,7 +566,8 @@ int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind) {
 
 int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_blocks,
                        int32_t* block_m, int32_t* block_stage, int32_t* block_slots,
-                       double* block_coef, int64_t* dest, double* fscale, double* iscale) {
+                       int32_t* block_final, double* coef_fwd, double* coef_inv, int64_t* dest,
+                       int64_t* rowbase) {
   return guarded([&] {
     if (!plan) throw InvalidArg("plan is null");
     if (k < 2 || k > plan->host.n) throw InvalidArg("level k must be in 2..n");
@@ -572,17 +579,17 @@ int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_bloc
       const Block& blk = P.blocks[b];
       if (block_m) block_m[b] = blk.m;
       if (block_stage) block_stage[b] = (int32_t)(b / P.d) + 1;
+      if (block_final) block_final[b] = blk.final_mask;
       if (block_slots)
         for (int x = 0; x < kMaxBlock; ++x) block_slots[b * kMaxBlock + x] = x < blk.m ? blk.slot[x] : -1;
-      if (block_coef) {
-        std::fill(block_coef + b * 25, block_coef + (b + 1) * 25, 0.0);
-        for (int x = 0; x < blk.m * blk.m; ++x) block_coef[b * 25 + x] = L.coef[blk.coef + x];
+      for (int x = 0; x < 25; ++x) {
+        if (coef_fwd) coef_fwd[b * 25 + x] = x < blk.m * blk.m ? L.coef[blk.coef_f + x] : 0.0;
+        if (coef_inv) coef_inv[b * 25 + x] = x < blk.m * blk.m ? L.coef[blk.coef_i + x] : 0.0;
       }
     }
     for (size_t s = 0; s < P.dest.size(); ++s) {
       if (dest) dest[s] = P.dest[s];
-      if (fscale) fscale[s] = P.fscale[s];
-      if (iscale) iscale[s] = P.iscale[s];
+      if (rowbase) rowbase[s] = P.rowbase[s];
     }
   });
 }

@@ -23,15 +23,10 @@ struct LevelDev {
   const PanelDev* panels;
   const Block* blocks;
   const double* coef;
-  const uint32_t* dest;
-  const double* fscale;
-  const double* iscale;
-  const uint32_t* rowbase;
-  // only for levels handled by the fused shared-memory kernel (k <= 8), else null:
-  const uint32_t* item_tab;    // [(k-1)!] : (panel << 24) | (block-in-stage << 12) | column
-  const uint32_t* copy_dest;   // [k!] input position -> output position
-  const double* copy_fscale;   // [k!] forward scale of that row
-  const double* copy_iscale;   // [k!] inverse scale of that row
+  const uint32_t* dest;      // slot -> offset of the finished row in the k! output
+  const uint32_t* rowbase;   // slot -> offset of the row in the k! input
+  // only for the level run table-driven inside the fused kernel (k = 7), else null:
+  const uint32_t* item_tab;  // [(k-1)!] : (panel << 24) | (block-in-stage << 12) | column
 };
 
 // A unit of work of the streaming level kernel: columns [c0, c0+w) of one panel, `cap` groups per

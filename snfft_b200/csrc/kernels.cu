@@ -10,6 +10,8 @@
 // against HBM (16 B per element per pass) and shared-memory bandwidth.
 #include "kernels.cuh"
 
+#include "gen_small.cuh"
+
 #include <mutex>
 #include <vector>
 
@@ -89,41 +91,38 @@ namespace {
 constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
-// block executor: y = C x (forward) or y = C^T x (inverse) on m rows addressed by p[b]
+// table-driven block executor
 // ---------------------------------------------------------------------------------------------
-template <int M, bool INV>
-__device__ __forceinline__ void apply_block(double* __restrict__ base, const int* off,
-                                            const double* __restrict__ cm) {
-  double x[M], y[M];
-#pragma unroll
-  for (int b = 0; b < M; ++b) x[b] = base[off[b]];
+// floor(e / w) for 0 <= e < 2^20 with inv = 1/w (the +0.5 keeps the quotient off integer edges)
+__device__ __forceinline__ int fast_div(int e, float inv) {
+  return __float2int_rz(((float)e + 0.5f) * inv);
+}
+
+template <int M>
+__device__ __forceinline__ void matvec(const double* __restrict__ cm, const double (&x)[kMaxBlock],
+                                       double (&y)[kMaxBlock]) {
 #pragma unroll
   for (int a = 0; a < M; ++a) {
-    double acc = 0.0;
+    double acc = __ldg(cm + a * M) * x[0];
 #pragma unroll
-    for (int b = 0; b < M; ++b) {
-      const double c = INV ? __ldg(cm + b * M + a) : __ldg(cm + a * M + b);
-      acc = fma(c, x[b], acc);
-    }
+    for (int b = 1; b < M; ++b) acc = fma(__ldg(cm + a * M + b), x[b], acc);
     y[a] = acc;
   }
-#pragma unroll
-  for (int a = 0; a < M; ++a) base[off[a]] = y[a];
 }
 
-template <bool INV>
-__device__ __forceinline__ void dispatch_block(int m, double* base, const int* off,
-                                               const double* cm) {
+__device__ __forceinline__ void matvec_m(int m, const double* __restrict__ cm,
+                                         const double (&x)[kMaxBlock], double (&y)[kMaxBlock]) {
   switch (m) {
-    case 2: apply_block<2, INV>(base, off, cm); break;
-    case 3: apply_block<3, INV>(base, off, cm); break;
-    case 4: apply_block<4, INV>(base, off, cm); break;
-    default: apply_block<5, INV>(base, off, cm); break;
+    case 2: matvec<2>(cm, x, y); break;
+    case 3: matvec<3>(cm, x, y); break;
+    case 4: matvec<4>(cm, x, y); break;
+    default: matvec<5>(cm, x, y); break;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// streaming level kernel
+// streaming level kernel (any k): column tiles of one panel staged through shared memory, stages
+// in place, finished rows stored straight from registers.
 // grid.x = tiles of the level, grid.y = group chunks (grid-stride over groups)
 // ---------------------------------------------------------------------------------------------
 template <bool INV>
@@ -135,32 +134,20 @@ level_kernel(LevelDev L, const Tile* __restrict__ tiles, const double* __restric
   const PanelDev P = L.panels[t.panel];
   const int d = P.d, rows = P.rows, w = t.w, k = L.k;
   const uint32_t* __restrict__ dest = L.dest + P.slot_off;
-  const double* __restrict__ fscale = L.fscale + P.slot_off;
-  const double* __restrict__ iscale = L.iscale + P.slot_off;
+  const uint32_t* __restrict__ rowbase = L.rowbase + P.slot_off;
+  const uint32_t* __restrict__ first = INV ? dest : rowbase;  // where a slot's row is read from
   const int tile_elems = rows * w;
-  // forward reads the k packed S_{k-1} spectra of a group and writes the packed S_k spectrum;
-  // the inverse swaps the roles of the two buffers.
-  const double* __restrict__ src = in;
-  double* __restrict__ dst = out;
+  const float inv_w = 1.0f / (float)w, inv_tile = 1.0f / (float)tile_elems, inv_d = 1.0f / (float)d;
 
   for (int64_t g0 = (int64_t)blockIdx.y * t.cap; g0 < groups; g0 += (int64_t)gridDim.y * t.cap) {
     const int ng = (int)min((int64_t)t.cap, groups - g0);
-    // ---- load --------------------------------------------------------------------------------
+    // ---- stage the tile: buf[(gb * rows + slot) * w + c] -------------------------------------
     for (int e = threadIdx.x; e < ng * tile_elems; e += kThreads) {
-      const int gb = e / tile_elems;
+      const int gb = fast_div(e, inv_tile);
       const int r = e - gb * tile_elems;
-      const int s = r / w;
+      const int s = fast_div(r, inv_w);
       const int c = r - s * w;
-      const int64_t gbase = (g0 + gb) * (int64_t)L.kfact;
-      double v;
-      if (!INV) {
-        const int i = s / d;
-        const int u = s - i * d;
-        v = src[gbase + (int64_t)i * L.km1fact + P.in_off + u * d + t.c0 + c];
-      } else {
-        v = iscale[s] * src[gbase + dest[s] + t.c0 + c];
-      }
-      buf[e] = v;
+      buf[e] = in[(g0 + gb) * (int64_t)L.kfact + first[s] + t.c0 + c];
     }
     __syncthreads();
     // ---- stages ------------------------------------------------------------------------------
@@ -169,112 +156,234 @@ level_kernel(LevelDev L, const Tile* __restrict__ tiles, const double* __restric
       const Block* __restrict__ blocks = L.blocks + P.blk_off + stage * d;
       const int items = ng * d * w;
       for (int e = threadIdx.x; e < items; e += kThreads) {
-        const int c = e % w;
-        const int tq = e / w;
-        const int q = tq % d;
-        const int gb = tq / d;
+        const int tq = fast_div(e, inv_w);
+        const int c = e - tq * w;
+        const int gb = fast_div(tq, inv_d);
+        const int q = tq - gb * d;
         const Block b = blocks[q];
-        int off[kMaxBlock];
+        double* __restrict__ base = buf + gb * tile_elems + c;
+        double* __restrict__ gout = out + (g0 + gb) * (int64_t)L.kfact + t.c0 + c;
+        double x[kMaxBlock], y[kMaxBlock];
 #pragma unroll
-        for (int x = 0; x < kMaxBlock; ++x) off[x] = (int)b.slot[x] * w;
-        dispatch_block<INV>(b.m, buf + gb * tile_elems + c, off, L.coef + b.coef);
+        for (int i = 0; i < kMaxBlock; ++i)
+          if (i < b.m) x[i] = base[(int)b.slot[i] * w];
+        matvec_m(b.m, L.coef + (INV ? b.coef_i : b.coef_f), x, y);
+        if (!INV) {
+#pragma unroll
+          for (int i = 0; i < kMaxBlock; ++i)
+            if (i < b.m) {
+              if ((b.final_mask >> i) & 1)
+                gout[dest[b.slot[i]]] = y[i];
+              else
+                base[(int)b.slot[i] * w] = y[i];
+            }
+        } else {
+          gout[b.xoff] = y[0];  // X_{j+1}[W] is finished
+          if (b.xoff1 != 0xffffffffu)
+            gout[b.xoff1] = y[1];  // stage 1: X_1[W] too
+          else
+            base[(int)b.slot[1] * w] = y[1];
+#pragma unroll
+          for (int i = 2; i < kMaxBlock; ++i)
+            if (i < b.m) base[(int)b.slot[i] * w] = y[i];
+        }
       }
       __syncthreads();
     }
-    // ---- store -------------------------------------------------------------------------------
-    for (int e = threadIdx.x; e < ng * tile_elems; e += kThreads) {
-      const int gb = e / tile_elems;
-      const int r = e - gb * tile_elems;
-      const int s = r / w;
-      const int c = r - s * w;
-      const int64_t gbase = (g0 + gb) * (int64_t)L.kfact;
-      if (!INV) {
-        dst[gbase + dest[s] + t.c0 + c] = fscale[s] * buf[e];
-      } else {
-        const int i = s / d;
-        const int u = s - i * d;
-        dst[gbase + (int64_t)i * L.km1fact + P.in_off + u * d + t.c0 + c] = buf[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused low levels.  K0 = min(n, 7).  Levels 2..4 run in registers per S_4 block (24 values per
+// thread), levels 5 and 6 as generated whole-column register programs with one shared-memory
+// exchange each, level 7 as the table-driven executor in shared memory with finished rows stored
+// straight to global memory.  Shared-memory layouts are padded (gen::kS4/kS5/kP6/kS6) so that
+// consecutive sub-groups hit distinct banks.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedBuf = 6400;  // doubles per ping-pong buffer (256 S_4 blocks * 25)
+
+template <int K0>
+struct FusedShape {
+  static constexpr int kFact = K0 == 4 ? 24 : K0 == 5 ? 120 : K0 == 6 ? 720 : 5040;
+  static constexpr int kS4Blocks = kFact / 24;  // S_4 blocks per group
+  static constexpr int kGroups = K0 == 7 ? 1 : (K0 == 6 ? 8 : (K0 == 5 ? 51 : 256));  // per iteration
+};
+
+// all instances of one generated level (5 or 6): warp-tasks = (panel, 32 instances), instances
+// ordered sub-group fastest so that a warp touches consecutive sub-groups (distinct banks)
+template <int LEVEL, bool INV, class AddrIn, class AddrOut>
+__device__ __forceinline__ void run_generated_level(int nsub, AddrIn in_of, AddrOut out_of) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kThreads >> 5;
+  constexpr int np = LEVEL == 5 ? gen::kL5Panels : gen::kL6Panels;
+  int task = warp;  // round-robin over the flattened (panel, chunk) list
+  int seen = 0;
+#pragma unroll 1
+  for (int p = 0; p < np; ++p) {
+    const int dp = LEVEL == 5 ? gen::kL5Dims[p] : gen::kL6Dims[p];
+    const int ninst = nsub * dp;
+    const int chunks = (ninst + 31) >> 5;
+    while (task < seen + chunks) {
+      const int inst = (task - seen) * 32 + lane;
+      if (inst < ninst) {
+        const int c = inst / nsub;
+        const int g = inst - c * nsub;
+        if (LEVEL == 5)
+          gen::l5_run<INV>(p, in_of(g) + c, out_of(g) + c);
+        else
+          gen::l6_run<INV>(p, in_of(g) + c, out_of(g) + c);
       }
+      task += nwarps;
     }
-    __syncthreads();
+    seen += chunks;
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// fused low levels: one CTA per S_{k0} block, two ping-pong buffers of k0! doubles
-// ---------------------------------------------------------------------------------------------
-template <bool INV>
-__device__ __forceinline__ void fused_stage(const LevelDev& L, int stage, double* __restrict__ A,
-                                            int nsub) {
-  const int items = nsub * L.km1fact;
-  for (int e = threadIdx.x; e < items; e += kThreads) {
-    const int sub = e / L.km1fact;
-    const int r = e - sub * L.km1fact;
-    const uint32_t it = __ldg(L.item_tab + r);
-    const PanelDev P = L.panels[it >> 24];
-    const int q = (it >> 12) & 0xfff;
-    const int c = it & 0xfff;
-    const Block b = L.blocks[P.blk_off + stage * P.d + q];
-    const uint32_t* __restrict__ rowbase = L.rowbase + P.slot_off;
-    int off[kMaxBlock];
-#pragma unroll
-    for (int x = 0; x < kMaxBlock; ++x) off[x] = x < b.m ? (int)__ldg(rowbase + b.slot[x]) : 0;
-    dispatch_block<INV>(b.m, A + sub * L.kfact + c, off, L.coef + b.coef);
-  }
-}
-
-template <bool INV>
-__global__ void __launch_bounds__(kThreads)
+template <int K0, bool INV>
+__global__ void __launch_bounds__(kThreads, 2)
 fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in may alias out
   extern __shared__ double sm[];
-  const int n0 = F.k0fact;
-  double* A = sm;
-  double* B = sm + n0;
-  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-    const double* gin = in + g * n0;
-    double* gout = out + g * n0;
-    for (int e = threadIdx.x; e < n0; e += kThreads) A[e] = gin[e];
-    __syncthreads();
+  using S = FusedShape<K0>;
+  double* bufA = sm;
+  double* bufB = sm + kFusedBuf;
+  const LevelDev& L7 = F.level[7];
+
+  for (int64_t g0 = (int64_t)blockIdx.x * S::kGroups; g0 < groups; g0 += (int64_t)gridDim.x * S::kGroups) {
+    const int ng = (int)min((int64_t)S::kGroups, groups - g0);
+    const double* gin = in + g0 * S::kFact;
+    double* gout = out + g0 * S::kFact;
+    const int n4 = ng * S::kS4Blocks;  // S_4 blocks in this chunk (<= 256)
     if (!INV) {
-      for (int k = 2; k <= F.k0; ++k) {
-        const LevelDev& L = F.level[k];
-        const int nsub = n0 / L.kfact;
-        for (int st = 0; st < k - 1; ++st) {
-          fused_stage<false>(L, st, A, nsub);
-          __syncthreads();
+      // ---- levels 2..4 in registers -----------------------------------------------------------
+      if ((int)threadIdx.x < n4) {
+        double r[24];
+        const double* src = gin + (int64_t)threadIdx.x * 24;
+#pragma unroll
+        for (int i = 0; i < 24; i += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(src + i);
+          r[i] = v.x;
+          r[i + 1] = v.y;
         }
-        // packed layout of level k: B[sub][copy_dest[r]] = fscale[r] * A[sub][r]
-        for (int e = threadIdx.x; e < n0; e += kThreads) {
-          const int sub = e / L.kfact;
-          const int r = e - sub * L.kfact;
-          B[sub * L.kfact + __ldg(L.copy_dest + r)] = __ldg(L.copy_fscale + r) * A[e];
-        }
+        gen::s4_fwd(r);
+        double* dst = K0 == 4 ? gout + (int64_t)threadIdx.x * 24 : bufA + threadIdx.x * gen::kS4;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) dst[i] = r[i];
+      }
+      if (K0 >= 5) {
         __syncthreads();
-        double* tmp = A;
-        A = B;
-        B = tmp;
+        const int nsub = n4 / 5;
+        if (K0 == 5)
+          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)bufA + g * gen::kG5; },
+                                        [&](int g) { return gout + (int64_t)g * 120; });
+        else
+          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)bufA + g * gen::kG5; },
+                                        [&](int g) { return bufB + g * gen::kS5 + (g / 6) * gen::kP6; });
+      }
+      if (K0 >= 6) {
+        __syncthreads();
+        const int nsub = n4 / 30;
+        if (K0 == 6)
+          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)bufB + g * gen::kG6; },
+                                        [&](int g) { return gout + (int64_t)g * 720; });
+        else
+          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)bufB + g * gen::kG6; },
+                                        [&](int g) { return bufA + g * gen::kS6; });
+      }
+      if (K0 == 7) {
+        // ---- level 7: table-driven in shared memory, finished rows go to global memory --------
+        for (int st = 0; st < 6; ++st) {
+          __syncthreads();
+          for (int e = threadIdx.x; e < 720; e += kThreads) {
+            const uint32_t it = __ldg(L7.item_tab + e);
+            const PanelDev P = L7.panels[it >> 24];
+            const int q = (it >> 12) & 0xfff, c = it & 0xfff;
+            const Block b = L7.blocks[P.blk_off + st * P.d + q];
+            const uint32_t* __restrict__ rowbase = L7.rowbase + P.slot_off;
+            const uint32_t* __restrict__ dest = L7.dest + P.slot_off;
+            int off[kMaxBlock];
+            double x[kMaxBlock], y[kMaxBlock];
+#pragma unroll
+            for (int i = 0; i < kMaxBlock; ++i)
+              if (i < b.m) {
+                const int rb = (int)__ldg(rowbase + b.slot[i]);
+                off[i] = rb + (rb / 720) * (gen::kS6 - 720) + c;
+                x[i] = bufA[off[i]];
+              }
+            matvec_m(b.m, L7.coef + b.coef_f, x, y);
+#pragma unroll
+            for (int i = 0; i < kMaxBlock; ++i)
+              if (i < b.m) {
+                if ((b.final_mask >> i) & 1)
+                  gout[__ldg(dest + b.slot[i]) + c] = y[i];
+                else
+                  bufA[off[i]] = y[i];
+              }
+          }
+        }
       }
     } else {
-      for (int k = F.k0; k >= 2; --k) {
-        const LevelDev& L = F.level[k];
-        const int nsub = n0 / L.kfact;
-        for (int e = threadIdx.x; e < n0; e += kThreads) {
-          const int sub = e / L.kfact;
-          const int r = e - sub * L.kfact;
-          B[e] = __ldg(L.copy_iscale + r) * A[sub * L.kfact + __ldg(L.copy_dest + r)];
+      if (K0 == 7) {
+        // ---- level 7 backwards: packed spectrum staged in bufB, rows rebuilt in bufA ----------
+        for (int e = threadIdx.x; e < 5040; e += kThreads) bufB[e] = gin[e];
+        for (int st = 5; st >= 0; --st) {
+          __syncthreads();
+          for (int e = threadIdx.x; e < 720; e += kThreads) {
+            const uint32_t it = __ldg(L7.item_tab + e);
+            const PanelDev P = L7.panels[it >> 24];
+            const int q = (it >> 12) & 0xfff, c = it & 0xfff;
+            const Block b = L7.blocks[P.blk_off + st * P.d + q];
+            const uint32_t* __restrict__ rowbase = L7.rowbase + P.slot_off;
+            const uint32_t* __restrict__ dest = L7.dest + P.slot_off;
+            int off[kMaxBlock];
+            double x[kMaxBlock], y[kMaxBlock];
+#pragma unroll
+            for (int i = 0; i < kMaxBlock; ++i)
+              if (i < b.m) {
+                const int rb = (int)__ldg(rowbase + b.slot[i]);
+                off[i] = rb + (rb / 720) * (gen::kS6 - 720) + c;
+                x[i] = ((b.final_mask >> i) & 1) ? bufB[__ldg(dest + b.slot[i]) + c] : bufA[off[i]];
+              }
+            matvec_m(b.m, L7.coef + b.coef_i, x, y);
+#pragma unroll
+            for (int i = 0; i < kMaxBlock; ++i)
+              if (i < b.m) bufA[off[i]] = y[i];
+          }
         }
         __syncthreads();
-        for (int st = k - 2; st >= 0; --st) {
-          fused_stage<true>(L, st, B, nsub);
-          __syncthreads();
-        }
-        double* tmp = A;
-        A = B;
-        B = tmp;
+      }
+      if (K0 >= 6) {
+        const int nsub = n4 / 30;
+        if (K0 == 6)
+          run_generated_level<6, true>(nsub, [&](int g) { return gin + (int64_t)g * 720; },
+                                       [&](int g) { return bufB + g * gen::kG6; });
+        else
+          run_generated_level<6, true>(nsub, [&](int g) { return (const double*)bufA + g * gen::kS6; },
+                                       [&](int g) { return bufB + g * gen::kG6; });
+        __syncthreads();
+      }
+      if (K0 >= 5) {
+        const int nsub = n4 / 5;
+        if (K0 == 5)
+          run_generated_level<5, true>(nsub, [&](int g) { return gin + (int64_t)g * 120; },
+                                       [&](int g) { return bufA + g * gen::kG5; });
+        else
+          run_generated_level<5, true>(
+              nsub, [&](int g) { return (const double*)bufB + g * gen::kS5 + (g / 6) * gen::kP6; },
+              [&](int g) { return bufA + g * gen::kG5; });
+        __syncthreads();
+      }
+      if ((int)threadIdx.x < n4) {
+        double r[24];
+        const double* src = K0 == 4 ? gin + (int64_t)threadIdx.x * 24 : bufA + threadIdx.x * gen::kS4;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) r[i] = src[i];
+        gen::s4_inv(r);
+        double* dst = gout + (int64_t)threadIdx.x * 24;
+#pragma unroll
+        for (int i = 0; i < 24; i += 2)
+          *reinterpret_cast<double2*>(dst + i) = make_double2(r[i], r[i + 1]);
       }
     }
-    for (int e = threadIdx.x; e < n0; e += kThreads) gout[e] = A[e];
-    __syncthreads();
+    __syncthreads();  // buffers are reused by the next chunk
   }
 }
 
@@ -454,13 +563,25 @@ Facts make_facts() {
 
 }  // namespace
 
+namespace {
+template <class K>
+cudaError_t allow_big_smem(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+}  // namespace
+
 cudaError_t prepare_kernels() {
   cudaError_t e;
-  const int big = 227 * 1024;
-  if ((e = cudaFuncSetAttribute(level_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<4, true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<5, false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<5, true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<6, false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<6, true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<7, false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<7, true>)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -482,21 +603,31 @@ cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, s
   return cudaGetLastError();
 }
 
+template <int K0>
+static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* out, int64_t groups,
+                                   bool inverse, int num_sms, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)kFusedBuf * sizeof(double);
+  const int64_t per_iter = FusedShape<K0>::kGroups;
+  int64_t grid = (groups + per_iter - 1) / per_iter;
+  if (grid > 2LL * num_sms * 8) grid = 2LL * num_sms * 8;  // persistent beyond 8 waves
+  LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
+  if (inverse)
+    fused_kernel<K0, true><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
+  else
+    fused_kernel<K0, false><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fused(const FusedDev& F, const double* in, double* out, int64_t groups,
                          bool inverse, int num_sms, cudaStream_t stream) {
   if (groups <= 0) return cudaSuccess;
-  const size_t smem = 2 * (size_t)F.k0fact * sizeof(double);
-  int64_t per_sm = smem > 0 ? (200 * 1024) / (int64_t)smem : 8;
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  int64_t grid = (int64_t)num_sms * per_sm;
-  if (grid > groups) grid = groups;
-  LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
-  if (inverse)
-    fused_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
-  else
-    fused_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
-  return cudaGetLastError();
+  switch (F.k0) {
+    case 4: return launch_fused_k0<4>(F, in, out, groups, inverse, num_sms, stream);
+    case 5: return launch_fused_k0<5>(F, in, out, groups, inverse, num_sms, stream);
+    case 6: return launch_fused_k0<6>(F, in, out, groups, inverse, num_sms, stream);
+    case 7: return launch_fused_k0<7>(F, in, out, groups, inverse, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_build_lex_table(int n, uint32_t* table, cudaStream_t stream) {

@@ -123,9 +123,11 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
   }
 
   P.blocks.reserve((size_t)(k - 1) * d);
+  std::vector<std::vector<double>> raw_all;  // forward matrices of P.blocks, before folding
   for (int j = 1; j <= k - 1; ++j) {
     next.clear();
     std::vector<Block> stage;
+    std::vector<std::vector<double>> raw;  // unfolded forward matrices, same order as `stage`
     stage.reserve(d);
     for (int cw = 0; cw < d; ++cw) {
       const std::vector<uint8_t>& w = chains[cw];  // w[t] = id at level k-1-t
@@ -136,7 +138,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
       const int m = 1 + (int)sj.down.size();
       if (m != (int)sj.up.size() || m > kMaxBlock) throw std::runtime_error("bad block size");
       Block blk{};
-      blk.m = (uint16_t)m;
+      blk.m = (uint8_t)m;
       double scale[kMaxBlock];
       blk.slot[0] = (uint16_t)(j * d + cw);  // X_{j+1}[W]
       scale[0] = 1.0;
@@ -163,19 +165,11 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
         key.push_back((char)Wj);
         next[key] = RegVal{(int32_t)blk.slot[a], 1.0};
       }
-      auto ins = coef_index.find(cm);
-      if (ins == coef_index.end()) {
-        uint32_t off = (uint32_t)level.coef.size();
-        // keep every matrix 16-byte aligned
-        if (off & 1) {
-          level.coef.push_back(0.0);
-          ++off;
-        }
-        level.coef.insert(level.coef.end(), cm.begin(), cm.end());
-        ins = coef_index.emplace(cm, off).first;
-      }
-      blk.coef = ins->second;
+      blk.xoff = 0;
+      blk.xoff1 = 0xffffffffu;
+      blk.reserved = 0;
       stage.push_back(blk);
+      raw.push_back(cm);
       level.macs += (double)m * m * d;
     }
     // rows not consumed by a block: U^j != T^j, a pure scaling (folded into a pending scale)
@@ -199,18 +193,22 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
       nk.append(key, (size_t)j, key.size() - j - 1);
       next[nk] = RegVal{kv.second.slot, kv.second.scale * b};
     }
-    std::stable_sort(stage.begin(), stage.end(),
-                     [](const Block& a, const Block& b) { return a.m < b.m; });
-    P.blocks.insert(P.blocks.end(), stage.begin(), stage.end());
+    // blocks of equal size together (uniform warps); keep the matrices aligned with them
+    std::vector<int> order(stage.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return stage[a].m < stage[b].m; });
+    for (int i : order) {
+      P.blocks.push_back(stage[i]);
+      raw_all.push_back(raw[i]);
+    }
     reg.swap(next);
   }
 
   const int64_t rows = (int64_t)k * d;
   if ((int64_t)reg.size() != rows) throw std::runtime_error("row count mismatch at output");
   P.dest.assign(rows, 0);
-  P.fscale.assign(rows, 0.0);
-  P.iscale.assign(rows, 0.0);
   P.rowbase.assign(rows, 0);
+  std::vector<double> fscale(rows, 0.0), weight(rows, 0.0);
   std::vector<char> seen(rows, 0);
   for (auto& kv : reg) {
     const std::string& key = kv.first;  // T = (lambda, T^{k-1}, .., T^1), U = (mu)
@@ -223,12 +221,53 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
     if (seen[slot]) throw std::runtime_error("slot used twice");
     seen[slot] = 1;
     P.dest[slot] = (uint32_t)(sl.off + row * sl.dim + bmu.off);
-    P.fscale[slot] = kv.second.scale;
-    P.iscale[slot] = kv.second.scale * (double)sl.dim / ((double)k * (double)d);
+    fscale[slot] = kv.second.scale;
+    weight[slot] = (double)sl.dim / ((double)k * (double)d);  // L^-1 = L^T diag(d_lambda/(k d_mu))
   }
   for (int i = 0; i < k; ++i)
     for (int u = 0; u < d; ++u)
       P.rowbase[(size_t)i * d + u] = (uint32_t)(i * plan.fact[k - 1] + P.in_off + (int64_t)u * d);
+
+  // Fold the pending output scale of every slot into the block that writes it last, mark those
+  // outputs as final, and emit the forward / inverse coefficient matrices.
+  std::vector<int> last_writer(rows, -1);
+  for (size_t b = 0; b < P.blocks.size(); ++b)
+    for (int a = 0; a < P.blocks[b].m; ++a) last_writer[P.blocks[b].slot[a]] = (int)b;
+  for (int64_t s = 0; s < rows; ++s)
+    if (last_writer[s] < 0) throw std::runtime_error("slot is never written");
+  auto intern = [&](const std::vector<double>& cm) -> uint32_t {
+    auto it = coef_index.find(cm);
+    if (it != coef_index.end()) return it->second;
+    uint32_t off = (uint32_t)level.coef.size();
+    if (off & 1) {  // keep every matrix 16-byte aligned
+      level.coef.push_back(0.0);
+      ++off;
+    }
+    level.coef.insert(level.coef.end(), cm.begin(), cm.end());
+    coef_index.emplace(cm, off);
+    return off;
+  };
+  for (size_t b = 0; b < P.blocks.size(); ++b) {
+    Block& blk = P.blocks[b];
+    const int m = blk.m;
+    std::vector<double> F = raw_all[b], I((size_t)m * m);
+    blk.final_mask = 0;
+    for (int a = 0; a < m; ++a) {
+      const int slot = blk.slot[a];
+      double wgt = 1.0;
+      if (last_writer[slot] == (int)b) {
+        blk.final_mask |= (uint8_t)(1u << a);
+        for (int c = 0; c < m; ++c) F[(size_t)a * m + c] *= fscale[slot];
+        wgt = weight[slot];
+      }
+      for (int c = 0; c < m; ++c) I[(size_t)c * m + a] = F[(size_t)a * m + c] * wgt;
+    }
+    blk.coef_f = intern(F);
+    blk.coef_i = intern(I);
+    blk.xoff = P.rowbase[blk.slot[0]];
+    const int stage_of = (int)(b / d) + 1;
+    blk.xoff1 = stage_of == 1 ? P.rowbase[blk.slot[1]] : 0xffffffffu;
+  }
 }
 
 }  // namespace

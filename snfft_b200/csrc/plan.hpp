@@ -31,13 +31,24 @@ struct LevelShapes {
   std::vector<ShapeInfo> shapes;  // utils.partitions(k) order
 };
 
-// One small dense block of a stage: out[a] = sum_b coef[a][b] * in[b], in place on `slot`.
+// One small dense block of a stage, in place on `slot`:
+//   forward  out[a] = sum_b F[a][b] in[b]      (F at coef_f, row-major m x m)
+//   inverse  in[b]  = sum_a I[b][a] out[a]     (I at coef_i, row-major m x m)
+// I is F transposed with the Schur weights d_lambda/(k d_mu) folded in; all output scalings
+// (sqrt(1 - 1/dist^2) chains) are folded into F, so loads and stores never scale.
+// final_mask bit a: output a is the last write of its slot in the forward direction (equivalently
+// the first read of the inverse), i.e. it is the finished row that goes to `dest[slot]`.
 struct alignas(16) Block {
   uint16_t slot[kMaxBlock];
-  uint16_t m;
-  uint32_t coef;  // offset (in doubles) of the row-major m x m matrix in the level's pool
+  uint8_t m;
+  uint8_t final_mask;
+  uint32_t coef_f;  // offsets (in doubles) into the level's coefficient pool
+  uint32_t coef_i;
+  uint32_t xoff;    // offset in the k! input of the fresh row X_{j+1}[W] (slot[0]), start of its run
+  uint32_t xoff1;   // stage 1 only: offset of the X_1[W] row (slot[1]); else 0xffffffff
+  uint32_t reserved;
 };
-static_assert(sizeof(Block) == 16, "Block must be 16 bytes");
+static_assert(sizeof(Block) == 32, "Block must be 32 bytes");
 
 // Program of one column block mu |- k-1 of level k: k*d rows ("slots"), k-1 stages of d blocks.
 struct PanelProgram {
@@ -46,8 +57,6 @@ struct PanelProgram {
   int64_t in_off = 0;              // packed offset of mu in a level-(k-1) spectrum
   std::vector<Block> blocks;       // stage-major: stage s (1..k-1) is blocks[(s-1)*d, s*d)
   std::vector<uint32_t> dest;      // slot -> offset in the k! output (start of a run of d)
-  std::vector<double> fscale;      // slot -> scale applied when writing the forward output
-  std::vector<double> iscale;      // slot -> scale applied when loading the inverse input
   std::vector<uint32_t> rowbase;   // slot -> offset in the k! input (start of a run of d)
 };
 

@@ -89,21 +89,22 @@ class Plan:
         """Host copy of one panel program (see ``snfft_export_panel``)."""
         nb = C.c_int32()
         N.check(N.lib.snfft_export_panel(self._h, k, panel, C.byref(nb), None, None, None, None,
-                                         None, None, None))
+                                         None, None, None, None))
         nb = nb.value
         d = nb // (k - 1)
         m = np.zeros(nb, dtype=np.int32)
         stage = np.zeros(nb, dtype=np.int32)
         slots = np.zeros((nb, 5), dtype=np.int32)
-        coef = np.zeros((nb, 25), dtype=np.float64)
+        final = np.zeros(nb, dtype=np.int32)
+        coef_f = np.zeros((nb, 25), dtype=np.float64)
+        coef_i = np.zeros((nb, 25), dtype=np.float64)
         dest = np.zeros(k * d, dtype=np.int64)
-        fscale = np.zeros(k * d, dtype=np.float64)
-        iscale = np.zeros(k * d, dtype=np.float64)
+        rowbase = np.zeros(k * d, dtype=np.int64)
         N.check(N.lib.snfft_export_panel(self._h, k, panel, C.byref(C.c_int32()), N.ptr(m),
-                                         N.ptr(stage), N.ptr(slots), N.ptr(coef), N.ptr(dest),
-                                         N.ptr(fscale), N.ptr(iscale)))
-        return dict(d=d, m=m, stage=stage, slots=slots, coef=coef, dest=dest, fscale=fscale,
-                    iscale=iscale)
+                                         N.ptr(stage), N.ptr(slots), N.ptr(final), N.ptr(coef_f),
+                                         N.ptr(coef_i), N.ptr(dest), N.ptr(rowbase)))
+        return dict(d=d, m=m, stage=stage, slots=slots, final=final, coef_fwd=coef_f,
+                    coef_inv=coef_i, dest=dest, rowbase=rowbase)
 
     # ------------------------------------------------------------------ device transforms
     def _check(self, t, name, last=None):

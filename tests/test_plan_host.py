@@ -91,32 +91,35 @@ def test_yor_trans_tables_bit_exact(golden_small, n):
 
 
 def interpret_level(plan, k, x, inverse=False):
-    """Run the exported block programs of level k in numpy: [k, (k-1)!] <-> [k!]."""
+    """Run the exported block programs of level k in numpy: [k, (k-1)!] <-> [k!].
+    Forward: rows are read at `rowbase`, every finished output (final mask) lands at `dest`.
+    Inverse: rows are read at `dest`, blocks run backwards with the inverse matrices."""
     parts, dims, offs = plan.layout(k - 1)
     kf = math.factorial(k)
-    out = np.zeros(kf) if not inverse else np.zeros((k, kf // k))
+    flat_in = x.reshape(-1)
+    out = np.zeros(kf)
     for pi, (d, o) in enumerate(zip(dims, offs)):
         prog = plan.export_panel(k, pi)
         assert prog['d'] == d and len(prog['m']) == (k - 1) * d
-        assert sorted(set(prog['slots'][prog['slots'] >= 0])) == list(range(k * d)) or k == 2
-        stages = [np.nonzero(prog['stage'] == s)[0] for s in range(1, k)]
-        if not inverse:
-            buf = np.concatenate([x[i, o:o + d * d].reshape(d, d) for i in range(k)], axis=0)
-        else:
-            buf = np.stack([prog['iscale'][s] * x[prog['dest'][s]:prog['dest'][s] + d] for s in range(k * d)])
-        for blocks in (reversed(stages) if inverse else stages):
-            for b in blocks:
-                m = prog['m'][b]
-                sl = prog['slots'][b, :m]
-                cm = prog['coef'][b, :m * m].reshape(m, m)
-                buf[sl] = (cm.T if inverse else cm) @ buf[sl]
-        if not inverse:
-            for s in range(k * d):
-                out[prog['dest'][s]:prog['dest'][s] + d] = prog['fscale'][s] * buf[s]
-        else:
-            for i in range(k):
-                out[i, o:o + d * d] = buf[i * d:(i + 1) * d].reshape(-1)
-    return out
+        assert sorted(set(prog['slots'][prog['slots'] >= 0])) == list(range(k * d))
+        assert sorted(prog['rowbase'].tolist()) == sorted(i * (kf // k) + o + u * d for i in range(k) for u in range(d))
+        # every slot is finished exactly once
+        finals = [prog['slots'][b, a] for b in range(len(prog['m'])) for a in range(prog['m'][b])
+                  if (prog['final'][b] >> a) & 1]
+        assert sorted(finals) == list(range(k * d))
+        src = prog['dest'] if inverse else prog['rowbase']
+        dst = prog['rowbase'] if inverse else prog['dest']
+        buf = np.stack([flat_in[src[s]:src[s] + d] for s in range(k * d)])
+        order = range(len(prog['m']))
+        assert list(prog['stage']) == sorted(prog['stage'])
+        for b in (reversed(order) if inverse else order):
+            m = prog['m'][b]
+            sl = prog['slots'][b, :m]
+            cm = prog['coef_inv' if inverse else 'coef_fwd'][b, :m * m].reshape(m, m)
+            buf[sl] = cm @ buf[sl]
+        for s in range(k * d):
+            out[dst[s]:dst[s] + d] = buf[s]
+    return out if not inverse else out.reshape(k, kf // k)
 
 
 @pytest.mark.parametrize('n', range(2, 8))
