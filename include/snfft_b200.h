@@ -133,6 +133,11 @@ double snfft_level_macs_per_element(const snfft_plan* plan, int k);
  * gpu_launches claim is read from here). */
 int64_t snfft_launch_count(void);
 
+/* Test hook: level 8 normally runs as generated register programs; on != 0 routes it through the
+ * table-driven streaming kernel that serves k >= 9, so that tests can cover that kernel at a size
+ * the oracle reaches. */
+int snfft_debug_force_table_driven(int on);
+
 /* Per-kernel timing for bench.py: when enabled, every launch of this library is bracketed by CUDA
  * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[8] and
  * launches_by_kind[8] (0 fused forward, 1 fused inverse, 2 level forward, 3 level inverse,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "snfft_plan_device_bytes": (C.c_int64, [_p]),
     "snfft_level_macs_per_element": (C.c_double, [_p, C.c_int]),
     "snfft_launch_count": (C.c_int64, []),
+    "snfft_debug_force_table_driven": (C.c_int, [C.c_int]),
     "snfft_timing_enable": (C.c_int, [C.c_int]),
     "snfft_timing_read": (C.c_int, [_p, _p]),
     "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

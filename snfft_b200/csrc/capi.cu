@@ -552,6 +552,11 @@ double snfft_level_macs_per_element(const snfft_plan* plan, int k) {
 
 int64_t snfft_launch_count(void) { return g_launch_count; }
 
+int snfft_debug_force_table_driven(int on) {
+  g_force_table_driven = on != 0;
+  return SNFFT_OK;
+}
+
 int snfft_timing_enable(int on) {
   timing_enable(on != 0);
   return SNFFT_OK;

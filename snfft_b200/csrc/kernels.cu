@@ -12,12 +12,14 @@
 
 #include "gen_small.cuh"
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
 namespace snfft {
 
 int64_t g_launch_count = 0;
+bool g_force_table_driven = false;
 
 namespace {
 struct TimedLaunch {
@@ -238,6 +240,57 @@ __device__ __forceinline__ void run_generated_level(int nsub, AddrIn in_of, Addr
   }
 }
 
+// Round-robin distribution of 32-instance chunks of a list of segments over the warps of the CTA:
+// body(segment, instance) runs with all lanes of a warp inside the same segment.
+template <class Count, class Body>
+__device__ __forceinline__ void for_each_chunk(int seg_begin, int seg_end, Count count, Body body) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kThreads >> 5;
+  int task = warp, seen = 0;
+#pragma unroll 1
+  for (int sgm = seg_begin; sgm < seg_end; ++sgm) {
+    const int n = count(sgm);
+    const int chunks = (n + 31) >> 5;
+    while (task < seen + chunks) {
+      const int inst = (task - seen) * 32 + lane;
+      if (inst < n) body(sgm, inst);
+      task += nwarps;
+    }
+    seen += chunks;
+  }
+}
+
+// level 7 inside the fused kernel (one S_7 group): phase 1 turns the rows X_1..X_5 of every upper
+// chain (bufA, padded S_6 blocks) into C_5 rows (bufB, kind layout, panel region at 5*in_off);
+// phase 2 combines them with X_6, X_7 and stores the finished rows to global memory.
+template <bool INV>
+__device__ __forceinline__ void fused_level7_phase1(double* bufA, double* bufB) {
+  for_each_chunk(
+      0, 7, [](int sigma) { return gen::kL7P1SigmaStart[sigma + 1] - gen::kL7P1SigmaStart[sigma]; },
+      [&](int sigma, int inst) {
+        const int at = gen::kL7P1SigmaStart[sigma] + inst;
+        const int e = gen::kL7P1InstEntry[at], c = gen::kL7P1InstCol[at];
+        const int dmu = gen::kL7P1DMu[e], in_off = gen::kL7P1InOff[e], ubase = gen::kL7P1Base[e];
+        double* xrows = bufA + in_off + ubase * dmu + c;          // rows (i, t): i * kS6 + t * dmu
+        double* crows = bufB + 5 * in_off + 5 * ubase * dmu + c;  // rows p: p * dmu
+        if (!INV)
+          gen::p1_run<false>(sigma, xrows, gen::kS6, dmu, crows, 0, dmu);
+        else
+          gen::p1_run<true>(sigma, crows, 0, dmu, xrows, gen::kS6, dmu);
+      });
+}
+
+template <bool INV>
+__device__ __forceinline__ void fused_level7_phase2(double* bufA, double* bufB, double* gspec) {
+  for_each_chunk(
+      0, gen::kL7P2Programs, [](int pid) { return gen::kL7P2DRho[pid] * gen::kL7P2DMu[pid]; },
+      [&](int pid, int inst) {
+        const int dmu = gen::kL7P2DMu[pid], in_off = gen::kL7P2InOff[pid];
+        const int shift = inst / dmu, c = inst - shift * dmu;
+        gen::l7p2_run<INV>(pid, bufB + 5 * in_off + shift * dmu + c, dmu,
+                           bufA + in_off + shift * dmu + c, gen::kS6, dmu, gspec + c, shift);
+      });
+}
+
 template <int K0, bool INV>
 __global__ void __launch_bounds__(kThreads, 2)
 fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in may alias out
@@ -245,7 +298,6 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
   using S = FusedShape<K0>;
   double* bufA = sm;
   double* bufB = sm + kFusedBuf;
-  const LevelDev& L7 = F.level[7];
 
   for (int64_t g0 = (int64_t)blockIdx.x * S::kGroups; g0 < groups; g0 += (int64_t)gridDim.x * S::kGroups) {
     const int ng = (int)min((int64_t)S::kGroups, groups - g0);
@@ -289,65 +341,18 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
                                         [&](int g) { return bufA + g * gen::kS6; });
       }
       if (K0 == 7) {
-        // ---- level 7: table-driven in shared memory, finished rows go to global memory --------
-        for (int st = 0; st < 6; ++st) {
-          __syncthreads();
-          for (int e = threadIdx.x; e < 720; e += kThreads) {
-            const uint32_t it = __ldg(L7.item_tab + e);
-            const PanelDev P = L7.panels[it >> 24];
-            const int q = (it >> 12) & 0xfff, c = it & 0xfff;
-            const Block b = L7.blocks[P.blk_off + st * P.d + q];
-            const uint32_t* __restrict__ rowbase = L7.rowbase + P.slot_off;
-            const uint32_t* __restrict__ dest = L7.dest + P.slot_off;
-            int off[kMaxBlock];
-            double x[kMaxBlock], y[kMaxBlock];
-#pragma unroll
-            for (int i = 0; i < kMaxBlock; ++i)
-              if (i < b.m) {
-                const int rb = (int)__ldg(rowbase + b.slot[i]);
-                off[i] = rb + (rb / 720) * (gen::kS6 - 720) + c;
-                x[i] = bufA[off[i]];
-              }
-            matvec_m(b.m, L7.coef + b.coef_f, x, y);
-#pragma unroll
-            for (int i = 0; i < kMaxBlock; ++i)
-              if (i < b.m) {
-                if ((b.final_mask >> i) & 1)
-                  gout[__ldg(dest + b.slot[i]) + c] = y[i];
-                else
-                  bufA[off[i]] = y[i];
-              }
-          }
-        }
+        // ---- level 7 as two register phases ---------------------------------------------------
+        __syncthreads();
+        fused_level7_phase1<false>(bufA, bufB);
+        __syncthreads();
+        fused_level7_phase2<false>(bufA, bufB, gout);
       }
     } else {
       if (K0 == 7) {
-        // ---- level 7 backwards: packed spectrum staged in bufB, rows rebuilt in bufA ----------
-        for (int e = threadIdx.x; e < 5040; e += kThreads) bufB[e] = gin[e];
-        for (int st = 5; st >= 0; --st) {
-          __syncthreads();
-          for (int e = threadIdx.x; e < 720; e += kThreads) {
-            const uint32_t it = __ldg(L7.item_tab + e);
-            const PanelDev P = L7.panels[it >> 24];
-            const int q = (it >> 12) & 0xfff, c = it & 0xfff;
-            const Block b = L7.blocks[P.blk_off + st * P.d + q];
-            const uint32_t* __restrict__ rowbase = L7.rowbase + P.slot_off;
-            const uint32_t* __restrict__ dest = L7.dest + P.slot_off;
-            int off[kMaxBlock];
-            double x[kMaxBlock], y[kMaxBlock];
-#pragma unroll
-            for (int i = 0; i < kMaxBlock; ++i)
-              if (i < b.m) {
-                const int rb = (int)__ldg(rowbase + b.slot[i]);
-                off[i] = rb + (rb / 720) * (gen::kS6 - 720) + c;
-                x[i] = ((b.final_mask >> i) & 1) ? bufB[__ldg(dest + b.slot[i]) + c] : bufA[off[i]];
-              }
-            matvec_m(b.m, L7.coef + b.coef_i, x, y);
-#pragma unroll
-            for (int i = 0; i < kMaxBlock; ++i)
-              if (i < b.m) bufA[off[i]] = y[i];
-          }
-        }
+        // ---- level 7 backwards: phase 2 reads the packed spectrum from global memory ------------
+        fused_level7_phase2<true>(bufA, bufB, const_cast<double*>(gin));
+        __syncthreads();
+        fused_level7_phase1<true>(bufA, bufB);
         __syncthreads();
       }
       if (K0 >= 6) {
@@ -384,6 +389,80 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
       }
     }
     __syncthreads();  // buffers are reused by the next chunk
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// level 8 as two register phases (generated programs).  One CTA = one panel mu |- 7 of `cap`
+// consecutive groups: phase 1 reads the rows X_1..X_5 of every upper chain straight from global
+// memory and leaves the C_5 rows in shared memory ([group][5 d rows][d columns]); phase 2 reads
+// them together with X_6..X_8 from global memory and stores the finished rows.  The inverse runs
+// phase 2 transposed first.
+// ---------------------------------------------------------------------------------------------
+struct L8Launch {
+  int first_cta[gen::kL8NumPanels + 1];  // CTAs [first_cta[p], first_cta[p+1]) work on panel order[p]
+  int order[gen::kL8NumPanels];          // panels, heaviest first
+  int cap[gen::kL8NumPanels];            // groups per CTA, indexed like `order`
+};
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreads, 2)
+level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict__ out, int64_t groups) {
+  extern __shared__ double cbuf[];
+  int slot = 0;
+  while (slot + 1 < gen::kL8NumPanels && (int)blockIdx.x >= launch.first_cta[slot + 1]) ++slot;
+  const int panel = launch.order[slot], cap = launch.cap[slot];
+  const int d = gen::kL8PanelDim[panel], in_off = gen::kL8PanelInOff[panel];
+  const int64_t g0 = (int64_t)((int)blockIdx.x - launch.first_cta[slot]) * cap;
+  const int ng = (int)min((int64_t)cap, groups - g0);
+  const int cgroup = 5 * d * d;  // C_5 rows of one group
+  // forward: in = 8 packed S_7 spectra per group, out = packed S_8 spectrum; inverse: swapped
+  const double* xin = in + g0 * 40320;
+  double* xout = out + g0 * 40320;
+
+  auto phase1 = [&]() {
+    for_each_chunk(
+        gen::kL8P1RunFirst[panel], gen::kL8P1RunFirst[panel + 1],
+        [&](int run) { return ng * (gen::kL8P1RunStart[run + 1] - gen::kL8P1RunStart[run]) * d; },
+        [&](int run, int inst) {
+          const int e0 = gen::kL8P1RunStart[run], ne = gen::kL8P1RunStart[run + 1] - e0;
+          const int t = inst / d, c = inst - t * d;
+          const int gb = t / ne, e = e0 + (t - gb * ne);
+          const int ubase = gen::kL8P1Base[e];
+          double* crows = cbuf + gb * cgroup + 5 * ubase * d + c;
+          const int64_t xoff = (int64_t)gb * 40320 + in_off + ubase * d + c;
+          if (!INV)
+            gen::p1_run<false>(gen::kL8P1Sigma[e], xin + xoff, 5040, d, crows, 0, d);
+          else
+            gen::p1_run<true>(gen::kL8P1Sigma[e], crows, 0, d, xout + xoff, 5040, d);
+        });
+  };
+  auto phase2 = [&]() {
+    for_each_chunk(
+        gen::kL8P2First[panel], gen::kL8P2First[panel + 1],
+        [&](int pid) { return ng * gen::kL8P2DRho[pid] * d; },
+        [&](int pid, int inst) {
+          const int t = inst / d, c = inst - t * d;
+          const int drho = gen::kL8P2DRho[pid];
+          const int gb = t / drho, shift = t - gb * drho;
+          double* crows = cbuf + gb * cgroup + shift * d + c;
+          const int64_t goff = (int64_t)gb * 40320;
+          if (!INV)
+            gen::l8p2_run<false>(pid, crows, d, const_cast<double*>(xin) + goff + in_off + shift * d + c, 5040, d,
+                                 xout + goff + c, shift);
+          else
+            gen::l8p2_run<true>(pid, crows, d, xout + goff + in_off + shift * d + c, 5040, d,
+                                const_cast<double*>(xin) + goff + c, shift);
+        });
+  };
+  if (!INV) {
+    phase1();
+    __syncthreads();
+    phase2();
+  } else {
+    phase2();
+    __syncthreads();
+    phase1();
   }
 }
 
@@ -574,6 +653,8 @@ cudaError_t prepare_kernels() {
   cudaError_t e;
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<5, false>)) != cudaSuccess) return e;
@@ -585,10 +666,43 @@ cudaError_t prepare_kernels() {
   return cudaSuccess;
 }
 
+namespace {
+constexpr int kL8SmemDoubles = 6144;  // >= 5 * 35 * 35: C_5 rows of the widest panel (49 KB)
+
+cudaError_t launch_level8(const double* in, double* out, int64_t groups, bool inverse, cudaStream_t stream) {
+  static const int dims[gen::kL8NumPanels] = {1, 6, 15, 20, 15, 6, 1, 14, 35, 35, 14, 21, 14, 21, 14};
+  L8Launch launch;
+  int order[gen::kL8NumPanels];
+  for (int p = 0; p < gen::kL8NumPanels; ++p) order[p] = p;
+  std::stable_sort(order, order + gen::kL8NumPanels, [&](int a, int b) { return dims[a] > dims[b]; });
+  int64_t total = 0;
+  for (int i = 0; i < gen::kL8NumPanels; ++i) {
+    const int d = dims[order[i]];
+    int cap = kL8SmemDoubles / (5 * d * d);
+    if (cap > 64) cap = 64;
+    if (cap < 1) cap = 1;
+    launch.order[i] = order[i];
+    launch.cap[i] = cap;
+    launch.first_cta[i] = (int)total;
+    total += (groups + cap - 1) / cap;
+  }
+  launch.first_cta[gen::kL8NumPanels] = (int)total;
+  if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+  const size_t smem = kL8SmemDoubles * sizeof(double);
+  if (inverse)
+    level8_kernel<true><<<(unsigned)total, kThreads, smem, stream>>>(launch, in, out, groups);
+  else
+    level8_kernel<false><<<(unsigned)total, kThreads, smem, stream>>>(launch, in, out, groups);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, size_t smem_bytes,
                          const double* in, double* out, int64_t groups, bool inverse, int num_sms,
                          cudaStream_t stream) {
   if (groups <= 0 || ntiles <= 0) return cudaSuccess;
+  if (L.k == 8 && !g_force_table_driven) return launch_level8(in, out, groups, inverse, stream);
   // enough CTAs to fill the machine a few times over; each CTA strides over group chunks
   int64_t y = (8LL * num_sms + ntiles - 1) / ntiles;
   if (y > groups) y = groups;

@@ -8,6 +8,7 @@
 namespace snfft {
 
 extern int64_t g_launch_count;
+extern bool g_force_table_driven;  // tests: route level 8 through the table-driven kernel too
 
 // Optional per-launch timing (bench.py): when enabled every launch is bracketed by CUDA events on
 // its own stream; timing_read() synchronises the recorded events and returns the totals per kind.

@@ -128,6 +128,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
     next.clear();
     std::vector<Block> stage;
     std::vector<std::vector<double>> raw;  // unfolded forward matrices, same order as `stage`
+    std::vector<int> chain_of;             // chain index of each block of `stage`
     stage.reserve(d);
     for (int cw = 0; cw < d; ++cw) {
       const std::vector<uint8_t>& w = chains[cw];  // w[t] = id at level k-1-t
@@ -170,6 +171,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
       blk.reserved = 0;
       stage.push_back(blk);
       raw.push_back(cm);
+      chain_of.push_back(cw);
       level.macs += (double)m * m * d;
     }
     // rows not consumed by a block: U^j != T^j, a pure scaling (folded into a pending scale)
@@ -200,15 +202,61 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
     for (int i : order) {
       P.blocks.push_back(stage[i]);
       raw_all.push_back(raw[i]);
+      P.block_chain.push_back(chain_of[i]);
     }
     reg.swap(next);
+    if (j == 4 && k >= 6) {
+      // boundary of the two-phase split: every live row C_5[(T^5, T^4..T^1); ...] belongs to the
+      // group of its lower tableau (T^4..T^1); rows X_i[W], i > 5, to the group of W's lower part
+      P.low_rho.assign((size_t)k * d, -1);
+      P.low_idx.assign((size_t)k * d, -1);
+      P.c5_t5.assign((size_t)k * d, -1);
+      P.c5_u4.assign((size_t)k * d, -1);
+      P.c5_ubase.assign((size_t)k * d, -1);
+      P.c5_scale.assign((size_t)k * d, 1.0);
+      for (auto& kv : reg) {
+        const uint8_t* T = (const uint8_t*)kv.first.data();  // T^5, T^4, .., T^1
+        const uint8_t* U = T + 5;                            // U^{k-1}, .., U^5, U^4
+        const int slot = kv.second.slot;
+        P.low_rho[slot] = T[1];
+        P.low_idx[slot] = (int32_t)chain_index(plan, 4, T + 1);
+        P.c5_t5[slot] = T[0];
+        P.c5_u4[slot] = U[k - 5];
+        P.c5_scale[slot] = kv.second.scale;
+        // first chain below the upper part (U^{k-1}, .., U^5): offsets of the steps above level 5
+        int64_t base = 0;
+        for (int lev = k - 1; lev >= 6; --lev) base += find_down(plan, lev, U[k - 1 - lev], U[k - lev]).off;
+        P.c5_ubase[slot] = (int32_t)base;
+      }
+      for (int cw = 0; cw < d; ++cw) {
+        const std::vector<uint8_t>& w = chains[cw];
+        const uint8_t* low = &w[k - 1 - 4];  // W^4, .., W^1
+        for (int i = 5; i < k; ++i) {
+          P.low_rho[(size_t)i * d + cw] = low[0];
+          P.low_idx[(size_t)i * d + cw] = (int32_t)chain_index(plan, 4, low);
+        }
+      }
+    }
   }
 
   const int64_t rows = (int64_t)k * d;
   if ((int64_t)reg.size() != rows) throw std::runtime_error("row count mismatch at output");
   P.dest.assign(rows, 0);
   P.rowbase.assign(rows, 0);
-  std::vector<double> fscale(rows, 0.0), weight(rows, 0.0);
+  std::vector<double>& fscale = P.fscale;
+  std::vector<double>& weight = P.weight;
+  fscale.assign(rows, 0.0);
+  weight.assign(rows, 0.0);
+  P.lam_dim.assign(rows, 0);
+  if (k >= 6) {
+    P.chain_sigma.resize(d);
+    P.chain_base.resize(d);
+    for (int cw = 0; cw < d; ++cw) {
+      const std::vector<uint8_t>& w = chains[cw];
+      P.chain_sigma[cw] = w[k - 1 - 5];
+      P.chain_base[cw] = cw - (int32_t)chain_index(plan, 5, &w[k - 1 - 5]);
+    }
+  }
   std::vector<char> seen(rows, 0);
   for (auto& kv : reg) {
     const std::string& key = kv.first;  // T = (lambda, T^{k-1}, .., T^1), U = (mu)
@@ -223,6 +271,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
     P.dest[slot] = (uint32_t)(sl.off + row * sl.dim + bmu.off);
     fscale[slot] = kv.second.scale;
     weight[slot] = (double)sl.dim / ((double)k * (double)d);  // L^-1 = L^T diag(d_lambda/(k d_mu))
+    P.lam_dim[slot] = (int32_t)sl.dim;
   }
   for (int i = 0; i < k; ++i)
     for (int u = 0; u < d; ++u)
@@ -264,6 +313,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
     }
     blk.coef_f = intern(F);
     blk.coef_i = intern(I);
+    P.coef_raw.push_back(intern(raw_all[b]));
     blk.xoff = P.rowbase[blk.slot[0]];
     const int stage_of = (int)(b / d) + 1;
     blk.xoff1 = stage_of == 1 ? P.rowbase[blk.slot[1]] : 0xffffffffu;

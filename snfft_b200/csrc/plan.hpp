@@ -58,6 +58,24 @@ struct PanelProgram {
   std::vector<Block> blocks;       // stage-major: stage s (1..k-1) is blocks[(s-1)*d, s*d)
   std::vector<uint32_t> dest;      // slot -> offset in the k! output (start of a run of d)
   std::vector<uint32_t> rowbase;   // slot -> offset in the k! input (start of a run of d)
+  // ---- host-only metadata for the code generator (gen_programs.cpp) ----
+  std::vector<uint32_t> coef_raw;  // per block: forward matrix before the final scales are folded in
+  std::vector<int32_t> block_chain;  // per block: index of its chain W in tab(mu)
+  std::vector<double> fscale;      // slot -> pending scale of the finished row (folded into coef_f)
+  std::vector<double> weight;      // slot -> d_lambda / (k d_mu)
+  std::vector<int32_t> lam_dim;    // slot -> d_lambda of the finished row (row pitch of dest)
+  // two-phase split at stage 5 (k >= 6): rows are closed under stages 1..4 inside one
+  // "upper chain" (mu > .. > W^5) and under stages >= 5 inside one lower tableau of size 4
+  std::vector<int32_t> low_rho;    // slot -> id (partitions(4) order) of the shape of its lower tableau
+  std::vector<int32_t> low_idx;    // slot -> index of that lower tableau inside tab(rho)
+  // identity of the C_5 row held by a slot after stage 4 (-1 for rows X_i, i > 5):
+  // C_5[(T^5, rho, t) ; (upper chain .., U^5, U^4)]
+  std::vector<int32_t> c5_t5;      // id of T^5 (partitions(5) order)
+  std::vector<int32_t> c5_u4;      // id of U^4 (partitions(4) order)
+  std::vector<int32_t> c5_ubase;   // first chain index of the upper chain (mu > .. > U^5)
+  std::vector<double> c5_scale;    // pending scale of that C_5 row at the boundary (1 for X rows)
+  std::vector<int32_t> chain_sigma;  // chain -> id of W^5 (partitions(5) order)
+  std::vector<int32_t> chain_base;   // chain -> first index of the chains sharing its upper part down to W^5
 };
 
 struct LevelProgram {

@@ -82,9 +82,18 @@ def test_inverse_matches_oracle_and_round_trip(n):
     assert rel_fro(plan.inverse(plan.forward(x, 'coset'), 'coset').cpu().numpy(), f) < TOL
 
 
+@pytest.fixture
+def table_driven():
+    """Route level 8 through the table-driven streaming kernel (the one that serves k >= 9)."""
+    from snfft_b200 import _native as N
+    N.lib.snfft_debug_force_table_driven(1)
+    yield
+    N.lib.snfft_debug_force_table_driven(0)
+
+
 @pytest.mark.parametrize('n', range(2, 9))
-def test_streaming_level_kernel_every_level(n):
-    """snfft_level (the streaming kernel) applied level by level equals the fused path."""
+def test_streaming_level_kernel_every_level(n, table_driven):
+    """snfft_level (the table-driven streaming kernel) applied level by level equals the fused path."""
     plan = get_plan(n)
     f = np.random.default_rng(7 * n).standard_normal((2, math.factorial(n)))
     ref = O.pack(O.fft_all(f), n)
