@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libsnfft_b200.so")
+LIB_PATH = os.environ.get("SNFFT_B200_LIB") or os.path.join(_HERE, "_lib", "libsnfft_b200.so")
 
 SNFFT_OK = 0
 ORDER_COSET = 0

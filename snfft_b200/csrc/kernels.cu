@@ -91,6 +91,17 @@ void timing_read(double* ms_by_kind, int64_t* launches_by_kind) {
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef SNFFT_FUSED_THREADS
+#define SNFFT_FUSED_THREADS 384
+#endif
+#ifndef SNFFT_L8_MINBLOCKS
+#define SNFFT_L8_MINBLOCKS 2
+#endif
+#ifndef SNFFT_L8_THREADS
+#define SNFFT_L8_THREADS 256
+#endif
+constexpr int kL8Threads = SNFFT_L8_THREADS;
+constexpr int kFusedThreads = SNFFT_FUSED_THREADS;
 
 // ---------------------------------------------------------------------------------------------
 // table-driven block executor
@@ -202,20 +213,24 @@ level_kernel(LevelDev L, const Tile* __restrict__ tiles, const double* __restric
 // straight to global memory.  Shared-memory layouts are padded (gen::kS4/kS5/kP6/kS6) so that
 // consecutive sub-groups hit distinct banks.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFusedBuf = 6400;  // doubles per ping-pong buffer (256 S_4 blocks * 25)
+// Shared memory of the fused kernel: P holds padded S_4 / S_6 blocks, Q holds padded S_5 blocks,
+// then the C_5 rows of level 7 (3600) followed by the staged packed S_7 spectrum (5040).
+constexpr int kFusedP = 5256;  // >= 210 * kS4
+constexpr int kFusedQ = 8640;  // >= 3600 + 5040 and >= 42 * kS5 + 7
+constexpr int kFusedC = 3600;  // C_5 region of level 7 at the start of Q
 
 template <int K0>
 struct FusedShape {
   static constexpr int kFact = K0 == 4 ? 24 : K0 == 5 ? 120 : K0 == 6 ? 720 : 5040;
-  static constexpr int kS4Blocks = kFact / 24;  // S_4 blocks per group
-  static constexpr int kGroups = K0 == 7 ? 1 : (K0 == 6 ? 8 : (K0 == 5 ? 51 : 256));  // per iteration
+  static constexpr int kS4Blocks = kFact / 24;      // S_4 blocks per group
+  static constexpr int kGroups = 210 / kS4Blocks;   // groups per iteration (210 S_4 blocks)
 };
 
 // all instances of one generated level (5 or 6): warp-tasks = (panel, 32 instances), instances
 // ordered sub-group fastest so that a warp touches consecutive sub-groups (distinct banks)
 template <int LEVEL, bool INV, class AddrIn, class AddrOut>
 __device__ __forceinline__ void run_generated_level(int nsub, AddrIn in_of, AddrOut out_of) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kThreads >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   constexpr int np = LEVEL == 5 ? gen::kL5Panels : gen::kL6Panels;
   int task = warp;  // round-robin over the flattened (panel, chunk) list
   int seen = 0;
@@ -244,7 +259,7 @@ __device__ __forceinline__ void run_generated_level(int nsub, AddrIn in_of, Addr
 // body(segment, instance) runs with all lanes of a warp inside the same segment.
 template <class Count, class Body>
 __device__ __forceinline__ void for_each_chunk(int seg_begin, int seg_end, Count count, Body body) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kThreads >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   int task = warp, seen = 0;
 #pragma unroll 1
   for (int sgm = seg_begin; sgm < seg_end; ++sgm) {
@@ -273,9 +288,9 @@ __device__ __forceinline__ void fused_level7_phase1(double* bufA, double* bufB) 
         double* xrows = bufA + in_off + ubase * dmu + c;          // rows (i, t): i * kS6 + t * dmu
         double* crows = bufB + 5 * in_off + 5 * ubase * dmu + c;  // rows p: p * dmu
         if (!INV)
-          gen::p1_run<false>(sigma, xrows, gen::kS6, dmu, crows, 0, dmu);
+          gen::p1_run<false, gen::kS6>(sigma, xrows, dmu, crows, dmu);
         else
-          gen::p1_run<true>(sigma, crows, 0, dmu, xrows, gen::kS6, dmu);
+          gen::p1_run<true, gen::kS6>(sigma, crows, dmu, xrows, dmu);
       });
 }
 
@@ -286,106 +301,148 @@ __device__ __forceinline__ void fused_level7_phase2(double* bufA, double* bufB, 
       [&](int pid, int inst) {
         const int dmu = gen::kL7P2DMu[pid], in_off = gen::kL7P2InOff[pid];
         const int shift = inst / dmu, c = inst - shift * dmu;
-        gen::l7p2_run<INV>(pid, bufB + 5 * in_off + shift * dmu + c, dmu,
-                           bufA + in_off + shift * dmu + c, gen::kS6, dmu, gspec + c, shift);
+        gen::l7p2_run<INV>(pid, bufB + 5 * in_off + shift * dmu + c, bufA + in_off + shift * dmu + c,
+                           gspec + c, shift);
       });
 }
 
 template <int K0, bool INV>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 2)
 fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in may alias out
   extern __shared__ double sm[];
   using S = FusedShape<K0>;
-  double* bufA = sm;
-  double* bufB = sm + kFusedBuf;
+  double* P = sm;
+  double* Q = sm + kFusedP;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
 
   for (int64_t g0 = (int64_t)blockIdx.x * S::kGroups; g0 < groups; g0 += (int64_t)gridDim.x * S::kGroups) {
     const int ng = (int)min((int64_t)S::kGroups, groups - g0);
     const double* gin = in + g0 * S::kFact;
     double* gout = out + g0 * S::kFact;
-    const int n4 = ng * S::kS4Blocks;  // S_4 blocks in this chunk (<= 256)
+    const int n4 = ng * S::kS4Blocks;  // S_4 blocks in this chunk (<= 210)
+    const int nelem = n4 * 24;
     if (!INV) {
-      // ---- levels 2..4 in registers -----------------------------------------------------------
-      if ((int)threadIdx.x < n4) {
-        double r[24];
-        const double* src = gin + (int64_t)threadIdx.x * 24;
+      // ---- coalesced stage-in: S_4 blocks padded to stride kS4 ---------------------------------
+      if (K0 == 7) {
+        // all loads of the thread in flight before the first store (the group is 5040 doubles)
+        constexpr int kPer = (5040 + kFusedThreads - 1) / kFusedThreads;
+        double v[kPer];
 #pragma unroll
-        for (int i = 0; i < 24; i += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(src + i);
-          r[i] = v.x;
-          r[i + 1] = v.y;
+        for (int j = 0; j < kPer; ++j) {
+          const int e = tid + j * kFusedThreads;
+          v[j] = e < 5040 ? __ldg(gin + e) : 0.0;
         }
-        gen::s4_fwd(r);
-        double* dst = K0 == 4 ? gout + (int64_t)threadIdx.x * 24 : bufA + threadIdx.x * gen::kS4;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) dst[i] = r[i];
+        for (int j = 0; j < kPer; ++j) {
+          const int e = tid + j * kFusedThreads;
+          const int b = e / 24;
+          if (e < 5040) P[b * gen::kS4 + (e - b * 24)] = v[j];
+        }
+      } else {
+        for (int e = tid; e < nelem; e += nthreads) {
+          const int b = e / 24;
+          P[b * gen::kS4 + (e - b * 24)] = gin[e];
+        }
+      }
+      __syncthreads();
+      // ---- levels 2..4 in registers, in place ---------------------------------------------------
+      if (tid < n4) {
+        double r[24];
+        double* blk = P + tid * gen::kS4;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) r[i] = blk[i];
+        gen::s4_fwd(r);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) blk[i] = r[i];
+      }
+      __syncthreads();
+      if (K0 == 4) {
+        for (int e = tid; e < nelem; e += nthreads) {
+          const int b = e / 24;
+          gout[e] = P[b * gen::kS4 + (e - b * 24)];
+        }
       }
       if (K0 >= 5) {
-        __syncthreads();
         const int nsub = n4 / 5;
         if (K0 == 5)
-          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)bufA + g * gen::kG5; },
+          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)P + g * gen::kG5; },
                                         [&](int g) { return gout + (int64_t)g * 120; });
         else
-          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)bufA + g * gen::kG5; },
-                                        [&](int g) { return bufB + g * gen::kS5 + (g / 6) * gen::kP6; });
+          run_generated_level<5, false>(nsub, [&](int g) { return (const double*)P + g * gen::kG5; },
+                                        [&](int g) { return Q + g * gen::kS5 + (g / 6) * gen::kP6; });
       }
       if (K0 >= 6) {
         __syncthreads();
         const int nsub = n4 / 30;
         if (K0 == 6)
-          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)bufB + g * gen::kG6; },
+          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)Q + g * gen::kG6; },
                                         [&](int g) { return gout + (int64_t)g * 720; });
         else
-          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)bufB + g * gen::kG6; },
-                                        [&](int g) { return bufA + g * gen::kS6; });
+          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)Q + g * gen::kG6; },
+                                        [&](int g) { return P + g * gen::kS6; });
       }
       if (K0 == 7) {
-        // ---- level 7 as two register phases ---------------------------------------------------
+        // ---- level 7 as two register phases; the finished spectrum is staged in Q and copied
+        //      out with coalesced stores ------------------------------------------------------
         __syncthreads();
-        fused_level7_phase1<false>(bufA, bufB);
+        fused_level7_phase1<false>(P, Q);
         __syncthreads();
-        fused_level7_phase2<false>(bufA, bufB, gout);
+        fused_level7_phase2<false>(P, Q, Q + kFusedC);
+        __syncthreads();
+        for (int e = tid; e < 5040 / 2; e += nthreads)
+          reinterpret_cast<double2*>(gout)[e] = reinterpret_cast<const double2*>(Q + kFusedC)[e];
       }
     } else {
       if (K0 == 7) {
-        // ---- level 7 backwards: phase 2 reads the packed spectrum from global memory ------------
-        fused_level7_phase2<true>(bufA, bufB, const_cast<double*>(gin));
+        for (int e = tid; e < 5040 / 2; e += nthreads)
+          reinterpret_cast<double2*>(Q + kFusedC)[e] = reinterpret_cast<const double2*>(gin)[e];
         __syncthreads();
-        fused_level7_phase1<true>(bufA, bufB);
+        fused_level7_phase2<true>(P, Q, Q + kFusedC);
+        __syncthreads();
+        fused_level7_phase1<true>(P, Q);
         __syncthreads();
       }
       if (K0 >= 6) {
         const int nsub = n4 / 30;
         if (K0 == 6)
           run_generated_level<6, true>(nsub, [&](int g) { return gin + (int64_t)g * 720; },
-                                       [&](int g) { return bufB + g * gen::kG6; });
+                                       [&](int g) { return Q + g * gen::kG6; });
         else
-          run_generated_level<6, true>(nsub, [&](int g) { return (const double*)bufA + g * gen::kS6; },
-                                       [&](int g) { return bufB + g * gen::kG6; });
+          run_generated_level<6, true>(nsub, [&](int g) { return (const double*)P + g * gen::kS6; },
+                                       [&](int g) { return Q + g * gen::kG6; });
         __syncthreads();
       }
       if (K0 >= 5) {
         const int nsub = n4 / 5;
         if (K0 == 5)
           run_generated_level<5, true>(nsub, [&](int g) { return gin + (int64_t)g * 120; },
-                                       [&](int g) { return bufA + g * gen::kG5; });
+                                       [&](int g) { return P + g * gen::kG5; });
         else
           run_generated_level<5, true>(
-              nsub, [&](int g) { return (const double*)bufB + g * gen::kS5 + (g / 6) * gen::kP6; },
-              [&](int g) { return bufA + g * gen::kG5; });
+              nsub, [&](int g) { return (const double*)Q + g * gen::kS5 + (g / 6) * gen::kP6; },
+              [&](int g) { return P + g * gen::kG5; });
         __syncthreads();
       }
-      if ((int)threadIdx.x < n4) {
+      if (K0 == 4) {
+        for (int e = tid; e < nelem; e += nthreads) {
+          const int b = e / 24;
+          P[b * gen::kS4 + (e - b * 24)] = gin[e];
+        }
+        __syncthreads();
+      }
+      if (tid < n4) {
         double r[24];
-        const double* src = K0 == 4 ? gin + (int64_t)threadIdx.x * 24 : bufA + threadIdx.x * gen::kS4;
+        double* blk = P + tid * gen::kS4;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) r[i] = src[i];
+        for (int i = 0; i < 24; ++i) r[i] = blk[i];
         gen::s4_inv(r);
-        double* dst = gout + (int64_t)threadIdx.x * 24;
 #pragma unroll
-        for (int i = 0; i < 24; i += 2)
-          *reinterpret_cast<double2*>(dst + i) = make_double2(r[i], r[i + 1]);
+        for (int i = 0; i < 24; ++i) blk[i] = r[i];
+      }
+      __syncthreads();
+      for (int e = tid; e < nelem; e += nthreads) {
+        const int b = e / 24;
+        gout[e] = P[b * gen::kS4 + (e - b * 24)];
       }
     }
     __syncthreads();  // buffers are reused by the next chunk
@@ -406,7 +463,7 @@ struct L8Launch {
 };
 
 template <bool INV>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kL8Threads, SNFFT_L8_MINBLOCKS)
 level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict__ out, int64_t groups) {
   extern __shared__ double cbuf[];
   int slot = 0;
@@ -432,9 +489,9 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
           double* crows = cbuf + gb * cgroup + 5 * ubase * d + c;
           const int64_t xoff = (int64_t)gb * 40320 + in_off + ubase * d + c;
           if (!INV)
-            gen::p1_run<false>(gen::kL8P1Sigma[e], xin + xoff, 5040, d, crows, 0, d);
+            gen::p1_run<false, 5040>(gen::kL8P1Sigma[e], xin + xoff, d, crows, d);
           else
-            gen::p1_run<true>(gen::kL8P1Sigma[e], crows, 0, d, xout + xoff, 5040, d);
+            gen::p1_run<true, 5040>(gen::kL8P1Sigma[e], crows, d, xout + xoff, d);
         });
   };
   auto phase2 = [&]() {
@@ -448,10 +505,10 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
           double* crows = cbuf + gb * cgroup + shift * d + c;
           const int64_t goff = (int64_t)gb * 40320;
           if (!INV)
-            gen::l8p2_run<false>(pid, crows, d, const_cast<double*>(xin) + goff + in_off + shift * d + c, 5040, d,
+            gen::l8p2_run<false>(pid, crows, const_cast<double*>(xin) + goff + in_off + shift * d + c,
                                  xout + goff + c, shift);
           else
-            gen::l8p2_run<true>(pid, crows, d, xout + goff + in_off + shift * d + c, 5040, d,
+            gen::l8p2_run<true>(pid, crows, xout + goff + in_off + shift * d + c,
                                 const_cast<double*>(xin) + goff + c, shift);
         });
   };
@@ -691,9 +748,9 @@ cudaError_t launch_level8(const double* in, double* out, int64_t groups, bool in
   LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
   const size_t smem = kL8SmemDoubles * sizeof(double);
   if (inverse)
-    level8_kernel<true><<<(unsigned)total, kThreads, smem, stream>>>(launch, in, out, groups);
+    level8_kernel<true><<<(unsigned)total, kL8Threads, smem, stream>>>(launch, in, out, groups);
   else
-    level8_kernel<false><<<(unsigned)total, kThreads, smem, stream>>>(launch, in, out, groups);
+    level8_kernel<false><<<(unsigned)total, kL8Threads, smem, stream>>>(launch, in, out, groups);
   return cudaGetLastError();
 }
 }  // namespace
@@ -720,15 +777,15 @@ cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, s
 template <int K0>
 static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* out, int64_t groups,
                                    bool inverse, int num_sms, cudaStream_t stream) {
-  const size_t smem = 2 * (size_t)kFusedBuf * sizeof(double);
+  const size_t smem = (size_t)(kFusedP + kFusedQ) * sizeof(double);
   const int64_t per_iter = FusedShape<K0>::kGroups;
   int64_t grid = (groups + per_iter - 1) / per_iter;
   if (grid > 2LL * num_sms * 8) grid = 2LL * num_sms * 8;  // persistent beyond 8 waves
   LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
   if (inverse)
-    fused_kernel<K0, true><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
+    fused_kernel<K0, true><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
   else
-    fused_kernel<K0, false><<<(unsigned)grid, kThreads, smem, stream>>>(F, in, out, groups);
+    fused_kernel<K0, false><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
   return cudaGetLastError();
 }
 
