@@ -92,7 +92,7 @@ namespace {
 
 constexpr int kThreads = 256;
 #ifndef SNFFT_FUSED_THREADS
-#define SNFFT_FUSED_THREADS 384
+#define SNFFT_FUSED_THREADS 256
 #endif
 #ifndef SNFFT_L8_MINBLOCKS
 #define SNFFT_L8_MINBLOCKS 2
@@ -297,13 +297,8 @@ __device__ __forceinline__ void fused_level7_phase1(double* bufA, double* bufB) 
 template <bool INV>
 __device__ __forceinline__ void fused_level7_phase2(double* bufA, double* bufB, double* gspec) {
   for_each_chunk(
-      0, gen::kL7P2Programs, [](int pid) { return gen::kL7P2DRho[pid] * gen::kL7P2DMu[pid]; },
-      [&](int pid, int inst) {
-        const int dmu = gen::kL7P2DMu[pid], in_off = gen::kL7P2InOff[pid];
-        const int shift = inst / dmu, c = inst - shift * dmu;
-        gen::l7p2_run<INV>(pid, bufB + 5 * in_off + shift * dmu + c, bufA + in_off + shift * dmu + c,
-                           gspec + c, shift);
-      });
+      0, gen::kL7NumPanels, [](int panel) { return gen::kL7P2MaxInst[panel]; },
+      [&](int panel, int inst) { gen::l7p2_panel<INV>(panel, inst, bufB, bufA, gspec); });
 }
 
 template <int K0, bool INV>
