@@ -124,6 +124,40 @@ int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64
 int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, int64_t batch,
                      void* stream);
 
+/* ---- Sharded transform (multi-GPU) ----------------------------------------------
+ * The coset recursion of fft.py:96-98 splits S_n into n!/m! blocks of S_m (coset-major order puts
+ * them contiguously).  Rank r owns a contiguous range of blocks and runs levels 2..m on them with
+ * the ordinary plan of S_m.  Columns of f_hat are independent (the level step multiplies from the
+ * left), so ONE all-to-all then gives every rank all blocks but only "its" columns: for every
+ * nu |- m a contiguous range of the d_nu columns, and for larger shapes the union of the ranges of
+ * their branches.  Levels m+1..n run on these compact column shards without further
+ * communication; rank r ends with f_hat(lambda)[:, owned columns] for every lambda.  This replaces
+ * the gather-then-sum of cube_ft.py:102-106 (a reduce of full-size partial matrices) by an
+ * exchange that moves world-times fewer bytes.
+ * Compact level-k spectrum of rank r: for lambda in partitions(k) order, row-major
+ * d_lambda x w_r(lambda). */
+typedef struct snfft_shard snfft_shard;
+int snfft_shard_create(const snfft_plan* plan, int rank, int world, int m, snfft_shard** out);
+int snfft_shard_destroy(snfft_shard* shard);
+/* S_m blocks [*begin, *end) owned by rank r (of n!/m! blocks in coset-major order). */
+int snfft_shard_blocks(const snfft_shard* shard, int r, int64_t* begin, int64_t* end);
+/* Number of doubles of one compact level-k spectrum on rank r (m <= k <= n). */
+int snfft_shard_size(const snfft_shard* shard, int r, int k, int64_t* size);
+/* idx int64[size(r, m)]: positions inside a packed S_m spectrum of the entries that rank r needs
+ * (its columns of every nu |- m), in compact order: the send buffer for rank r is block[idx]. */
+int snfft_shard_gather_index(const snfft_shard* shard, int r, int64_t* idx);
+/* Columns of f_hat(irrep of S_k) owned by rank r, in compact order.  cols may be NULL. */
+int snfft_shard_columns(const snfft_shard* shard, int r, int k, int irrep, int32_t* cols, int32_t* count);
+/* One level k (m < k <= n) on the calling rank's shard: in double[groups][k][size(k-1)] ->
+ * out double[groups][size(k)] (inverse != 0: the other way). */
+int snfft_shard_level(const snfft_shard* shard, int k, const double* in_dev, double* out_dev,
+                      int64_t groups, int inverse, void* stream);
+/* Host export of the shard tables of one panel of level k (CPU tests): owned width, per-slot
+ * destination / input offsets in the compact layouts, and the group strides.  The blocks and
+ * coefficients are those of snfft_export_panel. */
+int snfft_shard_export_panel(const snfft_shard* shard, int k, int panel, int32_t* width, int64_t* dest,
+                             int64_t* rowbase, int64_t* in_stride, int64_t* out_stride);
+
 /* Sizes of the plan's tables, for DESIGN.md / tests: bytes on the device, and multiply-adds per
  * group element of level k (0 for k outside 2..n). */
 int64_t snfft_plan_device_bytes(const snfft_plan* plan);

@@ -59,6 +59,14 @@ SIGNATURES = {
     "snfft_coset_to_lex_host": (C.c_int, [_p, _p]),
     "snfft_yor": (C.c_int, [_p, C.c_int, _p, C.c_int64, _p, _p]),
     "snfft_dft_direct": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
+    "snfft_shard_create": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
+    "snfft_shard_destroy": (C.c_int, [_p]),
+    "snfft_shard_blocks": (C.c_int, [_p, C.c_int, _p, _p]),
+    "snfft_shard_size": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+    "snfft_shard_gather_index": (C.c_int, [_p, C.c_int, _p]),
+    "snfft_shard_columns": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "snfft_shard_level": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, C.c_int, _p]),
+    "snfft_shard_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
     "snfft_plan_device_bytes": (C.c_int64, [_p]),
     "snfft_level_macs_per_element": (C.c_double, [_p, C.c_int]),
     "snfft_launch_count": (C.c_int64, []),

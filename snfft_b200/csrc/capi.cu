@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -96,7 +97,9 @@ struct snfft_plan {
 
 namespace {
 
-void plan_tiles(const LevelProgram& prog, std::vector<Tile>& tiles, size_t& smem_bytes) {
+void plan_tiles(const LevelProgram& prog, const std::vector<int>& width, std::vector<Tile>& tiles,
+                size_t& smem_bytes) {
+  // width[p] = number of columns of panel p that are present (d_mu for a whole transform)
   // column tiling of every panel: whole panels when they fit in 48 KB, else column strips of up to
   // 96 KB (the widest strip that fits when even one column exceeds that).
   const int64_t kSmall = 6144, kLarge = 12288, kHard = (227 * 1024) / 8;
@@ -104,18 +107,20 @@ void plan_tiles(const LevelProgram& prog, std::vector<Tile>& tiles, size_t& smem
   for (size_t p = 0; p < prog.panels.size(); ++p) {
     const PanelProgram& P = prog.panels[p];
     const int64_t rows = (int64_t)P.k * P.d;
+    const int64_t cols = width[p];
+    if (cols == 0) continue;
     int64_t w;
-    if (rows * P.d <= kSmall) {
-      w = P.d;
+    if (rows * cols <= kSmall) {
+      w = cols;
     } else {
-      w = std::max<int64_t>(1, std::min<int64_t>(P.d, kLarge / rows));
-      const int64_t nt = (P.d + w - 1) / w;
-      w = (P.d + nt - 1) / nt;
+      w = std::max<int64_t>(1, std::min<int64_t>(cols, kLarge / rows));
+      const int64_t nt = (cols + w - 1) / w;
+      w = (cols + nt - 1) / nt;
     }
     if (rows * w > kHard) throw std::runtime_error("panel column does not fit in shared memory");
     level_elems = std::max(level_elems, rows * w);
-    for (int64_t c0 = 0; c0 < P.d; c0 += w)
-      tiles.push_back(Tile{(int32_t)p, (int32_t)c0, (int32_t)std::min<int64_t>(w, P.d - c0), 1});
+    for (int64_t c0 = 0; c0 < cols; c0 += w)
+      tiles.push_back(Tile{(int32_t)p, (int32_t)c0, (int32_t)std::min<int64_t>(w, cols - c0), 1});
   }
   for (Tile& t : tiles) {
     const PanelProgram& P = prog.panels[t.panel];
@@ -156,6 +161,8 @@ void upload_level(snfft_plan* plan, int k) {
   L.npanels = (int32_t)panels.size();
   L.kfact = (int32_t)plan->host.fact[k];
   L.km1fact = (int32_t)plan->host.fact[k - 1];
+  L.in_stride = plan->host.fact[k];
+  L.out_stride = plan->host.fact[k];
   L.panels = plan->upload(panels);
   L.blocks = plan->upload(blocks);
   L.coef = plan->upload(prog.coef);
@@ -173,7 +180,9 @@ void upload_level(snfft_plan* plan, int k) {
     L.item_tab = plan->upload(item_tab);
   }
   std::vector<Tile> tiles;
-  plan_tiles(prog, tiles, plan->level_smem[k]);
+  std::vector<int> width;
+  for (const PanelProgram& P : prog.panels) width.push_back(P.d);
+  plan_tiles(prog, width, tiles, plan->level_smem[k]);
   plan->ntiles[k] = (int)tiles.size();
   plan->tiles_dev[k] = plan->upload(tiles);
 }
@@ -238,6 +247,135 @@ YorTables& yor_tables_for(snfft_plan* plan, int irrep) {
   t.partner = plan->upload(partner);
   t.diag = plan->upload(diag);
   return plan->yor_tables.emplace(irrep, t).first->second;
+}
+
+}  // namespace
+
+
+// -----------------------------------------------------------------------------------------------
+// column shards (multi-GPU): see include/snfft_b200.h "Sharded transform"
+// -----------------------------------------------------------------------------------------------
+struct ShardLevel {
+  std::vector<int> width;           // per panel mu |- k-1: owned columns w_q(mu)
+  std::vector<int64_t> panel_off;   // per panel: offset of its compact block in a level-(k-1) spectrum
+  std::vector<uint32_t> dest, rowbase;  // concatenated over panels (like LevelDev)
+  std::vector<int> slot_off;        // per panel: first slot
+  LevelDev dev;
+  Tile* tiles_dev = nullptr;
+  int ntiles = 0;
+  size_t smem = 0;
+};
+
+struct snfft_shard {
+  const snfft_plan* plan = nullptr;
+  int rank = 0, world = 1, m = 0;
+  // w[q][k][shape]: owned columns of shape |- k (k >= m) on rank q; first[q][shape] for |shape| = m
+  std::vector<std::vector<std::vector<int>>> w;
+  std::vector<std::vector<int>> first;
+  std::vector<std::vector<int64_t>> size;  // size[q][k] = compact size of a level-k spectrum on rank q
+  std::vector<ShardLevel> levels;          // levels[k], k = m+1..n, for `rank`
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+int64_t shard_block_begin(int64_t nblocks, int world, int r) {
+  return (nblocks / world) * r + std::min<int64_t>(r, nblocks % world);
+}
+
+template <class T>
+T* shard_upload(snfft_shard* sh, const std::vector<T>& v) {
+  if (v.empty()) return nullptr;
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, v.size() * sizeof(T)));
+  sh->allocs.push_back(p);
+  CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return (T*)p;
+}
+
+// compact offset of shape `idx` inside a level-k spectrum of rank q
+int64_t shard_shape_off(const snfft_shard* sh, int q, int k, int idx) {
+  int64_t off = 0;
+  const auto& shapes = sh->plan->host.levels[k].shapes;
+  for (int i = 0; i < idx; ++i) off += shapes[i].dim * sh->w[q][k][i];
+  return off;
+}
+
+void build_shard_level(snfft_shard* sh, int k) {
+  const HostPlan& host = sh->plan->host;
+  const LevelProgram& prog = host.programs[k];
+  const int q = sh->rank;
+  ShardLevel& SL = sh->levels[k];
+  const int64_t s_in = sh->size[q][k - 1];
+  for (size_t p = 0; p < prog.panels.size(); ++p) {
+    const PanelProgram& P = prog.panels[p];
+    const int wq = sh->w[q][k - 1][p];
+    SL.width.push_back(wq);
+    SL.panel_off.push_back(shard_shape_off(sh, q, k - 1, (int)p));
+    SL.slot_off.push_back((int)SL.dest.size());
+    // finished row of slot s: (lambda, T) -> off_q(lambda) + row(T) * w_q(lambda) + columns of the
+    // branches of lambda that precede mu.  The unsharded dest is off(lambda) + row*d_lambda + off_lambda(mu).
+    for (int s = 0; s < P.k * P.d; ++s) {
+      const int i = s / P.d, u = s % P.d;
+      SL.rowbase.push_back((uint32_t)(i * s_in + SL.panel_off[p] + (int64_t)u * wq));
+      // recover (lambda, row) from the unsharded destination
+      const int64_t full = P.dest[s];
+      int lam = 0;
+      const auto& shapes = host.levels[k].shapes;
+      while (lam + 1 < (int)shapes.size() && shapes[lam + 1].off <= full) ++lam;
+      const int64_t rel = full - shapes[lam].off;
+      const int64_t row = rel / shapes[lam].dim;
+      int64_t coff = 0;
+      bool found = false;
+      for (const Branch& b : shapes[lam].down) {
+        if (b.idx == (int)p) {
+          found = true;
+          break;
+        }
+        coff += sh->w[q][k - 1][b.idx];
+      }
+      if (!found) throw std::runtime_error("shard: panel is not a branch of its output shape");
+      SL.dest.push_back((uint32_t)(shard_shape_off(sh, q, k, lam) + row * sh->w[q][k][lam] + coff));
+    }
+  }
+  if (sh->plan->device < 0) return;
+  // device tables: blocks are shared with the plan except for the input offsets used by the inverse
+  std::vector<PanelDev> panels;
+  std::vector<Block> blocks;
+  for (size_t p = 0; p < prog.panels.size(); ++p) {
+    const PanelProgram& P = prog.panels[p];
+    PanelDev pd;
+    pd.d = P.d;
+    pd.rows = P.k * P.d;
+    pd.in_off = (int32_t)SL.panel_off[p];
+    pd.blk_off = (int32_t)blocks.size();
+    pd.slot_off = SL.slot_off[p];
+    pd.item_off = 0;
+    panels.push_back(pd);
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      Block blk = P.blocks[b];
+      blk.xoff = SL.rowbase[SL.slot_off[p] + blk.slot[0]];
+      if (blk.xoff1 != 0xffffffffu) blk.xoff1 = SL.rowbase[SL.slot_off[p] + blk.slot[1]];
+      blocks.push_back(blk);
+    }
+  }
+  LevelDev& L = SL.dev;
+  L.k = k;
+  L.npanels = (int32_t)panels.size();
+  L.kfact = (int32_t)host.fact[k];
+  L.km1fact = (int32_t)host.fact[k - 1];
+  L.in_stride = (int64_t)k * s_in;
+  L.out_stride = sh->size[q][k];
+  L.panels = shard_upload(sh, panels);
+  L.blocks = shard_upload(sh, blocks);
+  L.coef = sh->plan->level_dev[k].coef;  // coefficient pool of the plan
+  L.dest = shard_upload(sh, SL.dest);
+  L.rowbase = shard_upload(sh, SL.rowbase);
+  L.item_tab = nullptr;
+  std::vector<Tile> tiles;
+  plan_tiles(prog, SL.width, tiles, SL.smem);
+  SL.ntiles = (int)tiles.size();
+  SL.tiles_dev = shard_upload(sh, tiles);
 }
 
 }  // namespace
@@ -540,6 +678,171 @@ int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, in
       plan->dft_matrix = R;
     }
     CUDA_OK(launch_dgemm(f_dev, plan->dft_matrix, fhat_dev, (int)batch, (int)nf, (int)nf, stream));
+  });
+}
+
+
+int snfft_shard_create(const snfft_plan* plan, int rank, int world, int m, snfft_shard** out) {
+  if (!out) {
+    g_last_error = "out is null";
+    return SNFFT_ERR_INVALID;
+  }
+  *out = nullptr;
+  snfft_shard* sh = nullptr;
+  int rc = guarded([&] {
+    if (!plan) throw InvalidArg("plan is null");
+    const int n = plan->host.n;
+    if (world < 1 || rank < 0 || rank >= world) throw InvalidArg("bad rank / world");
+    if (m < 1 || m >= n) throw InvalidArg("split level m must satisfy 1 <= m < n");
+    if (plan->host.fact[n] / plan->host.fact[m] < world) throw InvalidArg("fewer S_m blocks than ranks");
+    sh = new snfft_shard();
+    sh->plan = plan;
+    sh->rank = rank;
+    sh->world = world;
+    sh->m = m;
+    const HostPlan& host = plan->host;
+    sh->w.assign(world, std::vector<std::vector<int>>(n + 1));
+    sh->first.assign(world, {});
+    sh->size.assign(world, std::vector<int64_t>(n + 1, 0));
+    for (int q = 0; q < world; ++q) {
+      const auto& base = host.levels[m].shapes;
+      sh->w[q][m].resize(base.size());
+      sh->first[q].resize(base.size());
+      for (size_t i = 0; i < base.size(); ++i) {
+        const int64_t d = base[i].dim;
+        const int64_t a = d * q / world, b = d * (q + 1) / world;  // contiguous, nearly equal ranges
+        sh->first[q][i] = (int)a;
+        sh->w[q][m][i] = (int)(b - a);
+      }
+      for (int k = m + 1; k <= n; ++k) {
+        const auto& shapes = host.levels[k].shapes;
+        sh->w[q][k].assign(shapes.size(), 0);
+        for (size_t i = 0; i < shapes.size(); ++i)
+          for (const Branch& b : shapes[i].down) sh->w[q][k][i] += sh->w[q][k - 1][b.idx];
+      }
+      for (int k = m; k <= n; ++k) {
+        const auto& shapes = host.levels[k].shapes;
+        for (size_t i = 0; i < shapes.size(); ++i) sh->size[q][k] += shapes[i].dim * sh->w[q][k][i];
+        if (sh->size[q][k] > 0xffffffffLL) throw InvalidArg("shard too large for 32-bit offsets");
+      }
+    }
+    sh->levels.resize(n + 1);
+    std::unique_ptr<DeviceGuard> guard;
+    if (plan->device >= 0) guard.reset(new DeviceGuard(plan->device));
+    for (int k = m + 1; k <= n; ++k) build_shard_level(sh, k);
+  });
+  if (rc != SNFFT_OK) {
+    if (sh) snfft_shard_destroy(sh);
+    return rc;
+  }
+  *out = sh;
+  return SNFFT_OK;
+}
+
+int snfft_shard_destroy(snfft_shard* sh) {
+  if (!sh) return SNFFT_OK;
+  if (sh->plan && sh->plan->device >= 0) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(sh->plan->device);
+    for (void* p : sh->allocs) cudaFree(p);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  delete sh;
+  return SNFFT_OK;
+}
+
+int snfft_shard_blocks(const snfft_shard* sh, int r, int64_t* begin, int64_t* end) {
+  return guarded([&] {
+    if (!sh || !begin || !end) throw InvalidArg("null argument");
+    if (r < 0 || r >= sh->world) throw InvalidArg("rank out of range");
+    const HostPlan& host = sh->plan->host;
+    const int64_t nb = host.fact[host.n] / host.fact[sh->m];
+    *begin = shard_block_begin(nb, sh->world, r);
+    *end = shard_block_begin(nb, sh->world, r + 1);
+  });
+}
+
+int snfft_shard_size(const snfft_shard* sh, int r, int k, int64_t* size) {
+  return guarded([&] {
+    if (!sh || !size) throw InvalidArg("null argument");
+    if (r < 0 || r >= sh->world || k < sh->m || k > sh->plan->host.n) throw InvalidArg("rank or level out of range");
+    *size = sh->size[r][k];
+  });
+}
+
+int snfft_shard_gather_index(const snfft_shard* sh, int r, int64_t* idx) {
+  return guarded([&] {
+    if (!sh || !idx) throw InvalidArg("null argument");
+    if (r < 0 || r >= sh->world) throw InvalidArg("rank out of range");
+    const auto& shapes = sh->plan->host.levels[sh->m].shapes;
+    int64_t at = 0;
+    for (size_t i = 0; i < shapes.size(); ++i) {
+      const int64_t d = shapes[i].dim;
+      for (int64_t u = 0; u < d; ++u)
+        for (int c = 0; c < sh->w[r][sh->m][i]; ++c) idx[at++] = shapes[i].off + u * d + sh->first[r][i] + c;
+    }
+  });
+}
+
+namespace {
+void shard_columns_rec(const snfft_shard* sh, int r, int k, int idx, int base, std::vector<int32_t>& out) {
+  const ShapeInfo& s = sh->plan->host.levels[k].shapes[idx];
+  if (k == sh->m) {
+    for (int c = 0; c < sh->w[r][k][idx]; ++c) out.push_back(base + sh->first[r][idx] + c);
+    return;
+  }
+  for (const Branch& b : s.down) shard_columns_rec(sh, r, k - 1, b.idx, base + (int)b.off, out);
+}
+}  // namespace
+
+int snfft_shard_columns(const snfft_shard* sh, int r, int k, int irrep, int32_t* cols, int32_t* count) {
+  return guarded([&] {
+    if (!sh || !count) throw InvalidArg("null argument");
+    if (r < 0 || r >= sh->world || k < sh->m || k > sh->plan->host.n) throw InvalidArg("rank or level out of range");
+    if (irrep < 0 || irrep >= (int)sh->plan->host.levels[k].shapes.size()) throw InvalidArg("irrep out of range");
+    std::vector<int32_t> out;
+    shard_columns_rec(sh, r, k, irrep, 0, out);
+    if ((int)out.size() != sh->w[r][k][irrep]) throw std::runtime_error("shard: column count mismatch");
+    *count = (int32_t)out.size();
+    if (cols) std::copy(out.begin(), out.end(), cols);
+  });
+}
+
+int snfft_shard_level(const snfft_shard* sh, int k, const double* in_dev, double* out_dev, int64_t groups,
+                      int inverse, void* stream) {
+  return guarded([&] {
+    if (!sh) throw InvalidArg("shard is null");
+    require_device(sh->plan);
+    if (k <= sh->m || k > sh->plan->host.n) throw InvalidArg("level k must be in m+1..n");
+    if (!in_dev || !out_dev || in_dev == out_dev) throw InvalidArg("bad buffers");
+    if (groups < 0) throw InvalidArg("groups < 0");
+    DeviceGuard guard(sh->plan->device);
+    const ShardLevel& SL = sh->levels[k];
+    const bool saved = g_force_table_driven;
+    g_force_table_driven = true;  // the generated level-8 programs assume the full column pitch
+    cudaError_t e = launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, in_dev, out_dev, groups,
+                                 inverse != 0, sh->plan->num_sms, (cudaStream_t)stream);
+    g_force_table_driven = saved;
+    CUDA_OK(e);
+  });
+}
+
+int snfft_shard_export_panel(const snfft_shard* sh, int k, int panel, int32_t* width, int64_t* dest,
+                             int64_t* rowbase, int64_t* in_stride, int64_t* out_stride) {
+  return guarded([&] {
+    if (!sh) throw InvalidArg("shard is null");
+    if (k <= sh->m || k > sh->plan->host.n) throw InvalidArg("level k must be in m+1..n");
+    const ShardLevel& SL = sh->levels[k];
+    if (panel < 0 || panel >= (int)SL.width.size()) throw InvalidArg("panel out of range");
+    const PanelProgram& P = sh->plan->host.programs[k].panels[panel];
+    if (width) *width = SL.width[panel];
+    if (in_stride) *in_stride = (int64_t)k * sh->size[sh->rank][k - 1];
+    if (out_stride) *out_stride = sh->size[sh->rank][k];
+    for (int s = 0; s < P.k * P.d; ++s) {
+      if (dest) dest[s] = SL.dest[SL.slot_off[panel] + s];
+      if (rowbase) rowbase[s] = SL.rowbase[SL.slot_off[panel] + s];
+    }
   });
 }
 

@@ -20,6 +20,10 @@ struct LevelDev {
   int32_t npanels;
   int32_t kfact;    // k!
   int32_t km1fact;  // (k-1)!
+  // distance between consecutive groups on the input side (k sub-spectra) and on the output side
+  // (one spectrum); both k! for a whole transform, smaller for a column shard (snfft_shard_*)
+  int64_t in_stride;
+  int64_t out_stride;
   const PanelDev* panels;
   const Block* blocks;
   const double* coef;

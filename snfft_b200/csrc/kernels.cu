@@ -160,7 +160,7 @@ level_kernel(LevelDev L, const Tile* __restrict__ tiles, const double* __restric
       const int r = e - gb * tile_elems;
       const int s = fast_div(r, inv_w);
       const int c = r - s * w;
-      buf[e] = in[(g0 + gb) * (int64_t)L.kfact + first[s] + t.c0 + c];
+      buf[e] = in[(g0 + gb) * (INV ? L.out_stride : L.in_stride) + first[s] + t.c0 + c];
     }
     __syncthreads();
     // ---- stages ------------------------------------------------------------------------------
@@ -175,7 +175,7 @@ level_kernel(LevelDev L, const Tile* __restrict__ tiles, const double* __restric
         const int q = tq - gb * d;
         const Block b = blocks[q];
         double* __restrict__ base = buf + gb * tile_elems + c;
-        double* __restrict__ gout = out + (g0 + gb) * (int64_t)L.kfact + t.c0 + c;
+        double* __restrict__ gout = out + (g0 + gb) * (INV ? L.in_stride : L.out_stride) + t.c0 + c;
         double x[kMaxBlock], y[kMaxBlock];
 #pragma unroll
         for (int i = 0; i < kMaxBlock; ++i)
