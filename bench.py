@@ -162,16 +162,31 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     n, batch = WORKLOADS[args.workload]
     nf = math.factorial(n)
-    plan = get_plan(n, local)
     gen = torch.Generator(device=f'cuda:{local}').manual_seed(1234 + rank)
-    x = torch.randn(batch, nf, dtype=torch.float64, device=f'cuda:{local}', generator=gen)
-    spec = torch.empty_like(x)
-    back = torch.empty_like(x)
-    work = torch.empty_like(x)
+    # s10 / s12 on several GPUs: ONE function sharded by the coset recursion (strong scaling);
+    # otherwise every rank transforms its own batch (replicas, weak scaling)
+    sharded = world > 1 and args.workload != 's8'
+    if sharded:
+        from snfft_b200.sharded import ShardedPlan
+        batch = 1
+        plan = ShardedPlan(n, rank, world, device=local)
+        b, e = plan.local_elements()
+        x = torch.randn(e - b, dtype=torch.float64, device=f'cuda:{local}', generator=gen)
+        state = {}
 
-    def step():
-        plan.forward(x, 'coset', out=spec, work=work)
-        plan.inverse(spec, 'coset', out=back, work=work)
+        def step():
+            state['spec'] = plan.forward(x)
+            state['back'] = plan.inverse(state['spec'])
+    else:
+        plan = get_plan(n, local)
+        x = torch.randn(batch, nf, dtype=torch.float64, device=f'cuda:{local}', generator=gen)
+        spec = torch.empty_like(x)
+        back = torch.empty_like(x)
+        work = torch.empty_like(x)
+
+        def step():
+            plan.forward(x, 'coset', out=spec, work=work)
+            plan.inverse(spec, 'coset', out=back, work=work)
 
     def barrier():
         if world > 1:
@@ -181,6 +196,8 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if sharded:
+        back = state['back']
     err = ((back - x).norm() / x.norm()).item()
     assert err < 1e-10, f'round trip failed: {err}'
 
@@ -206,14 +223,16 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    elements_per_step = 2 * batch * nf * world           # both directions, all ranks
+    # both directions; replicas: every rank has its own batch, sharded: one function in total
+    elements_per_step = 2 * nf if sharded else 2 * batch * nf * world
     value = elements_per_step * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel, timed live over the timed region --------------------
     peak, peak_src = measured_peak_gbs()
     dom = max(kinds, key=lambda k: kinds[k][0])
     dom_ms, dom_cnt = kinds[dom]
-    bytes_per_launch = BYTES_PER_ELEMENT_PER_DIRECTION * batch * nf   # every pass reads + writes the batch
+    # every pass reads + writes this rank's share of the data
+    bytes_per_launch = BYTES_PER_ELEMENT_PER_DIRECTION * (nf // world if sharded else batch * nf)
     achieved = bytes_per_launch / (dom_ms / max(1, dom_cnt) * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     try:
@@ -230,17 +249,25 @@ def main():
                 'whole_step_frac': (2 * bytes_per_launch / (ms / args.steps * 1e-3) / 1e9) / peak}
 
     # ---- end to end from pinned host memory ------------------------------------------------------
-    hx = torch.empty((batch, nf), dtype=torch.float64).pin_memory()
+    hx = torch.empty(tuple(x.shape), dtype=torch.float64).pin_memory()
     hx.copy_(x.cpu())
-    hspec = torch.empty_like(hx).pin_memory()
+    if sharded:
+        hspec = torch.empty(state['spec'].shape, dtype=torch.float64).pin_memory()
+    else:
+        hspec = torch.empty_like(hx).pin_memory()
     hback = torch.empty_like(hx).pin_memory()
 
     def e2e_step():
         x.copy_(hx, non_blocking=True)
-        plan.forward(x, 'coset', out=spec, work=work)
-        hspec.copy_(spec, non_blocking=True)
-        plan.inverse(spec, 'coset', out=back, work=work)
-        hback.copy_(back, non_blocking=True)
+        if sharded:
+            sp = plan.forward(x)
+            hspec.copy_(sp, non_blocking=True)
+            hback.copy_(plan.inverse(sp), non_blocking=True)
+        else:
+            plan.forward(x, 'coset', out=spec, work=work)
+            hspec.copy_(spec, non_blocking=True)
+            plan.inverse(spec, 'coset', out=back, work=work)
+            hback.copy_(back, non_blocking=True)
 
     e2e_step()
     barrier()
@@ -272,7 +299,8 @@ def main():
         line = {
             'metric': 'S_n FFT elements/sec', 'value': value, 'unit': 'elements/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'higher_is_better': True, 'scaling': 'strong' if sharded else 'weak', 'vs_baseline': None,
+            'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': f'S_{n} forward+inverse FFT, batch {batch} per GPU '
                                    f'({"configs[1]" if args.workload == "s8" else args.workload})',
@@ -280,12 +308,13 @@ def main():
                        'directions_per_step': 2, 'order': 'coset-major',
                        'l2': f'inputs {batch * nf * 8 / 1e6:.0f} MB per buffer, larger than the 126 MB L2'
                              if batch * nf * 8 > 126e6 else 'working set fits L2: not an HBM number',
-                       'parallelism': f'batch-replicas x{world}' if world > 1 else 'single GPU',
+                       'parallelism': (f'coset-split column shards x{world}, one exchange' if sharded else
+                                       f'batch-replicas x{world}' if world > 1 else 'single GPU'),
                        'round_trip_rel_err': err},
             'roofline': roofline,
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'elements/s',
-                    'h2d_bytes_per_step': batch * nf * 8, 'd2h_bytes_per_step': 2 * batch * nf * 8},
+                    'h2d_bytes_per_step': x.numel() * 8, 'd2h_bytes_per_step': 2 * x.numel() * 8},
             'gpu_launches': launches,
             'clocks': clocks,
         }
