@@ -158,6 +158,17 @@ int snfft_shard_level(const snfft_shard* shard, int k, const double* in_dev, dou
 int snfft_shard_export_panel(const snfft_shard* shard, int k, int panel, int32_t* width, int64_t* dest,
                              int64_t* rowbase, int64_t* in_stride, int64_t* out_stride);
 
+/* ---- Building blocks of the wreath-product transform (wreath.py / multi.py / cube_ft.py) -------
+ * C[m,n] = A[m,k] B[k,n], fp64 row-major device matrices, on the DMMA tensor pipe
+ * (mma.sync.m8n8k4.f64).  The direct sums sum_g f(g) rho(g) of multi.py:25-46 and the character
+ * sums over orientations (wreath.py:43-58) are evaluated as such products. */
+int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t m, int64_t n, int64_t k,
+                void* stream);
+/* dst[e][0..width) = src[idx[e]][0..width) for e < count: regroups S_n by cosets of a Young
+ * subgroup (the double loop over coset representatives of wreath.py:304-313 as an index map). */
+int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev, int64_t count, int width,
+                 void* stream);
+
 /* Sizes of the plan's tables, for DESIGN.md / tests: bytes on the device, and multiply-adds per
  * group element of level k (0 for k outside 2..n). */
 int64_t snfft_plan_device_bytes(const snfft_plan* plan);

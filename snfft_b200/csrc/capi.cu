@@ -846,6 +846,25 @@ int snfft_shard_export_panel(const snfft_shard* sh, int k, int panel, int32_t* w
   });
 }
 
+int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t m, int64_t n, int64_t k,
+                void* stream) {
+  return guarded([&] {
+    if (!a_dev || !b_dev || !c_dev) throw InvalidArg("null device buffer");
+    if (m < 0 || n < 0 || k < 0 || m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff)
+      throw InvalidArg("bad GEMM shape");
+    CUDA_OK(launch_dgemm(a_dev, b_dev, c_dev, (int)m, (int)n, (int)k, (cudaStream_t)stream));
+  });
+}
+
+int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev, int64_t count, int width,
+                 void* stream) {
+  return guarded([&] {
+    if (!src_dev || !idx_dev || !dst_dev) throw InvalidArg("null device buffer");
+    if (count < 0 || width < 1) throw InvalidArg("bad gather shape");
+    CUDA_OK(launch_gather(src_dev, idx_dev, dst_dev, count, width, (cudaStream_t)stream));
+  });
+}
+
 int64_t snfft_plan_device_bytes(const snfft_plan* plan) { return plan ? plan->device_bytes : 0; }
 
 double snfft_level_macs_per_element(const snfft_plan* plan, int k) {

@@ -685,6 +685,15 @@ dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double*
     }
 }
 
+__global__ void gather_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx,
+                              double* __restrict__ dst, int64_t count, int width) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count * width;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / width;
+    dst[e] = src[idx[r] * width + (e - r * width)];
+  }
+}
+
 Facts make_facts() {
   Facts F;
   F.f[0] = 1;
@@ -827,6 +836,16 @@ cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
   if (count <= 0) return cudaSuccess;
   LaunchScope scope(kKindYor, stream);
   yor_kernel<<<(unsigned)count, kThreads, 0, stream>>>(n, d, partner, diag, perms, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,
+                          cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  int64_t blocks = (count * width + 255) / 256;
+  if (blocks > 65535 * 16) blocks = 65535 * 16;
+  LaunchScope scope(kKindOther, stream);
+  gather_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, idx, dst, count, width);
   return cudaGetLastError();
 }
 

@@ -40,6 +40,10 @@ cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
 cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K,
                          cudaStream_t stream);
 
+// dst[e][0..width) = src[idx[e]][0..width)
+cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,
+                          cudaStream_t stream);
+
 cudaError_t prepare_kernels();  // opt in to large dynamic shared memory (once per process)
 
 }  // namespace snfft

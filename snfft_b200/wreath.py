@@ -1,0 +1,303 @@
+"""Wreath-product (C_3 wr S_n, 2x2 cube) representations and their Fourier transform, with the
+reference's names (reference ``wreath.py``, ``multi.py``, ``cube_ft.py``, ``cube_ift.py``).
+
+rho(o, sigma) = D(o) P(sigma): P = Ind_{S_alpha}^{S_n}(kron_k rho_{parts_k}) as an N x N block
+matrix over the left cosets t_i S_alpha (block (i, j) present iff t_i^-1 sigma t_j in S_alpha,
+wreath.py:281-315) and D(o) the block-scalar matrix of cyclic characters (wreath.py:43-58,
+:123-143).  The transform  f_hat = sum_g f(g) rho(g)  (multi.py:25-46, cube_ft.py:53-61) factors
+into (1) character sums over the orientations, F_i(sigma) = sum_o f(o, sigma) chi_i(o), and (2) for
+every coset pair a sum over the Young subgroup, block(i, j) = sum_h F_i(t_i h t_j^-1) rho_parts(h)
+(SURVEY.md 7.0(10)); both are dense fp64 products evaluated on the DMMA tensor pipe
+(``snfft_dgemm``), regrouped by one index gather (``snfft_gather``).  All arithmetic is complex128
+(the reference uses complex64 scalars).  ``WreathPlan`` needs a CUDA device; the dictionary-based
+helpers (``wreath_yor``, ``get_mat``, ``wreath_rep``) are host-side glue like the reference's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import math
+from functools import reduce
+
+import numpy as np
+
+from . import _native as N
+from . import perm2
+from .coset_utils import (coset_reps, tup_set, young_coset_reps, young_subgroup, young_subgroup_perm)
+from .plan import get_plan
+from .utils import partitions
+from .yor import yor
+from .young_tableau import FerrersDiagram, wreath_dim
+
+
+# ---- group elements (wreath.py:14-121) -----------------------------------------------------------
+def dot(perm, cyc):
+    p_inv = perm.inv()
+    return CyclicGroup(tuple(cyc[p_inv[i] - 1] for i in range(1, len(cyc) + 1)), cyc.order)
+
+
+def dot_tup(perm, tup):
+    p_inv = perm.inv()
+    return tuple(tup[p_inv[i] - 1] for i in range(1, len(tup) + 1))
+
+
+def dot_tup_inv(perm, tup):
+    return tuple(tup[perm[i] - 1] for i in range(1, len(tup) + 1))
+
+
+class CyclicGroup:
+    def __init__(self, cyc, order):
+        self.cyc, self.size, self.order = tuple(cyc), len(cyc), order
+
+    @property
+    def tup_rep(self):
+        return self.cyc
+
+    def inv(self):
+        return CyclicGroup(tuple((self.order - a) % self.order for a in self.cyc), self.order)
+
+    def __mul__(self, other):
+        return CyclicGroup(tuple((a + b) % self.order for a, b in zip(self.cyc, other.cyc)), self.order)
+
+    __add__ = __mul__
+
+    def __len__(self):
+        return len(self.cyc)
+
+    def __getitem__(self, i):
+        return self.cyc[i]
+
+    def __repr__(self):
+        return '{}/{}'.format(self.cyc, self.order)
+
+
+class WreathCycSn:
+    """(o, sigma) with (o, s)(o', s') = (o + s.o', s s') (wreath.py:92-121)."""
+
+    def __init__(self, cyc, perm):
+        assert perm.size == len(cyc)
+        self.cyc, self.perm = cyc, perm
+
+    @property
+    def tup_rep(self):
+        return self.cyc.tup_rep, self.perm.tup_rep
+
+    @staticmethod
+    def from_tup(cyc_tup, perm_tup, order):
+        return WreathCycSn(CyclicGroup(cyc_tup, order), perm2.Perm2.from_tup(perm_tup))
+
+    def __mul__(self, w):
+        return WreathCycSn(self.cyc + dot(self.perm, w.cyc), self.perm * w.perm)
+
+    def inv(self):
+        p_inv = self.perm.inv()
+        return WreathCycSn(dot(p_inv, self.cyc.inv()), p_inv)
+
+    def inv_tup_rep(self):
+        return self.inv().tup_rep
+
+    def __repr__(self):
+        return '{} | {}'.format(self.cyc, self.perm)
+
+
+# ---- characters and induced blocks (wreath.py:43-58, :123-143, :175-224, :281-343, :387-394) -------
+def cyclic_irreps(weak_partition):
+    """tup -> exp(2 pi i (1*p2 + 2*p3)/3), p_k = sum of the k-th alpha-segment of tup."""
+    a, b = weak_partition[0], weak_partition[0] + weak_partition[1]
+
+    def func(tup):
+        return np.exp(2j * np.pi * (sum(tup[a:b]) + 2 * sum(tup[b:])) / 3.)
+    return func
+
+
+def block_cyclic_irreps(tup, coset_reps, cyclic_irrep_func):
+    """One scalar per coset representative (complex128; the reference stores complex64)."""
+    return np.array([cyclic_irrep_func(dot_tup_inv(rep, tup)) for rep in coset_reps], dtype=np.complex128)
+
+
+def canonical_order(tup_rep):
+    out, shift = [], 0
+    for lvl, tup in enumerate(tup_rep):
+        out.append(tup if lvl == 0 else tuple(shift + i for i in tup))
+        shift += len(tup)
+    return tuple(out)
+
+
+def young_subgroup_yor(alpha, _parts, prefix=None):
+    """{h in S_alpha as a permutation of 1..n: kron of the factors' YOR matrices}."""
+    nz = [(a, tuple(p)) for a, p in zip(alpha, _parts) if a > 0]
+    tables = []
+    for a, p in nz:
+        fd = FerrersDiagram.from_partition(p)
+        tables.append({t: yor(fd, perm2.Perm2.from_tup(t)) for t in itertools.permutations(range(1, a + 1))})
+    out = {}
+    for g in young_subgroup(alpha):
+        key = tuple(i for t in canonical_order(g) for i in t)
+        out[key] = reduce(np.kron, [tab[h] for tab, h in zip(tables, g)])
+    return out
+
+
+def wreath_yor(alpha, _parts, prefix=None):
+    """{sigma: {(i, j): block}} for every sigma in S_n (wreath.py:281-315).  Instead of scanning all
+    coset pairs per sigma, column j is found from the coset of sigma t_j."""
+    n = sum(alpha)
+    young_yor = young_subgroup_yor(alpha, _parts)
+    reps = [perm2.Perm2.from_tup(t) for t in young_coset_reps(alpha)]
+    index = {r.tup_rep: i for i, r in enumerate(reps)}
+    rep_dict = {}
+    for g in perm2.sn(n):
+        g_rep = {}
+        for j, t_j in enumerate(reps):
+            i = index[_coset_rep((g * t_j).tup_rep, alpha)]
+            g_rep[(i, j)] = young_yor[(reps[i].inv() * g * t_j).tup_rep]
+        rep_dict[g.tup_rep] = g_rep
+    return rep_dict
+
+
+def _coset_rep(tup, alpha):
+    """Representative of tup S_alpha: values sorted inside every alpha-segment."""
+    out, start = [], 0
+    for p in alpha:
+        out.extend(sorted(tup[start:start + p]))
+        start += p
+    return tuple(out)
+
+
+def get_mat(g, yor_dict, block_scalars=None):
+    yg = yor_dict[g if isinstance(g, tuple) else g.tup_rep]
+    block = next(iter(yg.values())).shape[0]
+    size = len(yg) * block
+    mat = np.zeros((size, size), dtype=np.complex128)
+    for (i, j), v in yg.items():
+        mat[block * i:block * (i + 1), block * j:block * (j + 1)] = (1 if block_scalars is None else block_scalars[i]) * v
+    return mat
+
+
+def wreath_rep(cyc_tup, perm, yor_dict, cos_reps, cyc_irrep_func=None, alpha=None):
+    if cyc_irrep_func is None and alpha is None:
+        raise ValueError('Need to supply either irrep func or alpha')
+    if cyc_irrep_func is None:
+        cyc_irrep_func = cyclic_irreps(alpha)
+    return get_mat(perm, yor_dict, block_cyclic_irreps(cyc_tup, cos_reps, cyc_irrep_func))
+
+
+# ---- the transform on the device ---------------------------------------------------------------------
+def _lex_ranks(perms):
+    """Lexicographic ranks of an int array of permutations [..., n] (1-based letters)."""
+    n = perms.shape[-1]
+    rank = np.zeros(perms.shape[:-1], dtype=np.int64)
+    for a in range(n):
+        smaller = (perms[..., a + 1:] < perms[..., a:a + 1]).sum(axis=-1)
+        rank += smaller * math.factorial(n - 1 - a)
+    return rank
+
+
+class WreathPlan:
+    """Fourier transform of functions on C_3^n x S_n (orientations restricted to ``oris``) at one
+    irrep (alpha, parts).  f is a float64 CUDA tensor [n!, len(oris)]: sigma in ``sn(n)`` order
+    (slow axis), orientation index (fast axis)."""
+
+    def __init__(self, alpha, parts, oris=None, device: int = 0):
+        import torch
+        self.alpha, self.parts, self.device = tuple(alpha), tuple(tuple(p) for p in parts), device
+        self.n = n = sum(alpha)
+        dev = f'cuda:{device}'
+        self.reps = young_coset_reps(self.alpha)
+        self.N = len(self.reps)
+        self.block = wreath_dim(self.parts)
+        self.D = self.N * self.block
+        if oris is None:
+            oris = [t for t in itertools.product((0, 1, 2), repeat=n) if sum(t) % 3 == 0]   # utils.py:206-209
+        self.oris = np.array(oris, dtype=np.int64).reshape(-1, n)
+        self.order = math.factorial(n) * len(self.oris)
+        # characters chi_i(o) (wreath.py:34-58): o o t_i summed over the alpha-segments
+        T = np.array(self.reps, dtype=np.int64)                       # [N, n]
+        a, b = self.alpha[0], self.alpha[0] + self.alpha[1]
+        og = self.oris[:, T - 1]                                      # [n_ori, N, n]
+        expo = (og[:, :, a:b].sum(-1) + 2 * og[:, :, b:].sum(-1)) % 3
+        omega = np.exp(2j * np.pi * np.arange(3) / 3.)
+        X = omega[expo]                                               # [n_ori, N]
+        self.Xre = torch.from_numpy(np.ascontiguousarray(X.real)).to(dev)
+        self.Xim = torch.from_numpy(np.ascontiguousarray(X.imag)).to(dev)
+        self.XreT = self.Xre.t().contiguous()
+        self.XimT = self.Xim.t().contiguous()
+        # R[h] = kron_k rho_{parts_k}(h_k), h in itertools.product order (wreath.py:191-224)
+        R = None
+        for ak, pk in zip(self.alpha, self.parts):
+            if ak == 0:
+                continue
+            plan = get_plan(ak, device)
+            perms = torch.tensor(list(itertools.permutations(range(1, ak + 1))), dtype=torch.int32, device=dev)
+            mats = plan.yor(plan.irrep_index(pk), perms)              # device YOR of the factor
+            if R is None:
+                R = mats
+            else:
+                R = torch.einsum('xab,ycd->xyacbd', R, mats).reshape(
+                    R.shape[0] * mats.shape[0], R.shape[1] * mats.shape[1], R.shape[2] * mats.shape[2])
+        self.nH = R.shape[0]
+        self.R = R.reshape(self.nH, self.block * self.block).contiguous()
+        self.RT = self.R.t().contiguous()
+        # sigma = t_i h t_j^-1 for every (i, j, h): one gather index into F[sigma][i]
+        H = np.array([p.tup_rep for p in young_subgroup_perm(self.alpha)], dtype=np.int64)   # [nH, n]
+        Tinv = np.argsort(T, axis=1) + 1
+        idx = np.empty((self.N, self.N, self.nH), dtype=np.int64)
+        for i in range(self.N):
+            hT = H[:, Tinv - 1]                                       # h(t_j^-1(p)) : [nH, N, n]
+            sig = T[i][hT - 1]                                        # t_i(h(t_j^-1(p)))
+            idx[i] = _lex_ranks(sig).T * self.N + i
+        flat = idx.reshape(-1)
+        inv = np.empty_like(flat)
+        inv[flat] = np.arange(flat.size)
+        self.idx = torch.from_numpy(flat).to(dev)
+        self.inv_idx = torch.from_numpy(inv).to(dev)
+
+    # -- thin wrappers over the C ABI
+    def _gemm(self, a, b):
+        import torch
+        m, k = a.shape
+        n = b.shape[1]
+        out = torch.empty((m, n), dtype=torch.float64, device=a.device)
+        N.check(N.lib.snfft_dgemm(N.ptr(a), N.ptr(b), N.ptr(out), m, n, k,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def _gather(self, src, idx):
+        import torch
+        out = torch.empty(idx.numel(), dtype=torch.float64, device=src.device)
+        N.check(N.lib.snfft_gather(N.ptr(src), N.ptr(idx), N.ptr(out), idx.numel(), 1,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def forward(self, f):
+        """complex128 [D, D] = sum_g f(g) rho(g)."""
+        import torch
+        if f.dtype != torch.float64 or not f.is_cuda or tuple(f.shape) != (math.factorial(self.n), len(self.oris)):
+            raise TypeError('f must be a float64 CUDA tensor [n!, n_orientations]')
+        f = f.contiguous()
+        with torch.cuda.device(self.device):
+            planes = []
+            for X in (self.Xre, self.Xim):
+                F = self._gemm(f, X)                                  # [n!, N]  character sums
+                G = self._gather(F.reshape(-1), self.idx)             # [N*N*nH] regrouped by cosets
+                planes.append(self._gemm(G.reshape(self.N * self.N, self.nH), self.R))
+        out = torch.complex(planes[0], planes[1]).reshape(self.N, self.N, self.block, self.block)
+        return out.permute(0, 2, 1, 3).reshape(self.D, self.D)
+
+    def inverse(self, fhat):
+        """complex128 [n!, n_ori]: D tr(rho(g)^H f_hat) / |G| at every group element
+        (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140)."""
+        import torch
+        B = fhat.reshape(self.N, self.block, self.N, self.block).permute(0, 2, 1, 3).reshape(
+            self.N * self.N, self.block * self.block)
+        with torch.cuda.device(self.device):
+            E = []
+            for plane in (B.real.contiguous(), B.imag.contiguous()):
+                e = self._gemm(plane, self.RT)                        # [N*N, nH]
+                E.append(self._gather(e.reshape(-1), self.inv_idx).reshape(math.factorial(self.n), self.N))
+            re = self._gemm(E[0], self.XreT) + self._gemm(E[1], self.XimT)
+            im = self._gemm(E[1], self.XreT) - self._gemm(E[0], self.XimT)
+        return torch.complex(re, im) * (self.D / self.order)
+
+
+def wreath_forward(f, alpha, parts, oris=None, device: int = 0):
+    return WreathPlan(alpha, parts, oris, device).forward(f)

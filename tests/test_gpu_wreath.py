@@ -1,0 +1,130 @@
+"""Wreath-product (C3 wr S_n) transform on the GPU against the complex128 oracle (1e-10) and the
+reference's golden vectors (1e-6: the reference works in complex64)."""
+import itertools
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import snfft_oracle as O
+import wreath_oracle as W
+from conftest import GOLDEN
+from snfft_b200 import perm2
+from snfft_b200.wreath import (WreathCycSn, WreathPlan, cyclic_irreps, get_mat, wreath_rep, wreath_yor)
+from snfft_b200.coset_utils import coset_reps, young_subgroup_perm
+
+pytestmark = pytest.mark.gpu
+CASES = [((0, 3, 2), ((), (2, 1), (1, 1))), ((1, 2, 2), ((1,), (1, 1), (2,))), ((2, 2, 1), ((2,), (1, 1), (1,)))]
+
+
+@pytest.mark.parametrize('ci', range(3))
+def test_forward_and_inverse_match_oracle(ci):
+    alpha, parts = CASES[ci]
+    n = sum(alpha)
+    golden = np.load(os.path.join(GOLDEN, 'reference_wreath.npz'))
+    oris = W.orientations(n)
+    f = np.random.default_rng(100 + ci).standard_normal((math.factorial(n), len(oris)))
+    wp = WreathPlan(alpha, parts)
+    assert [tuple(o) for o in wp.oris.tolist()] == oris
+    got = wp.forward(torch.from_numpy(f).cuda())
+    ref = W.wreath_ft_direct(alpha, parts, f, oris)
+    assert np.linalg.norm(got.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-10
+    assert np.linalg.norm(got.cpu().numpy() - golden[f'case{ci}_fhat']) / np.linalg.norm(ref) < 1e-6
+    inv = wp.inverse(got).cpu().numpy()
+    want = W.wreath_inverse_direct(alpha, parts, ref, oris, math.factorial(n) * len(oris))
+    assert np.abs(inv - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+
+
+def test_wreath_yor_homomorphism():
+    # test_wreath.py:16-35 with the reference-shaped helpers (dictionary of blocks per permutation)
+    alpha, parts = (0, 3, 2), ((), (2, 1), (1, 1))
+    ydict = wreath_yor(alpha, parts)
+    keys = list(ydict.keys())
+    rng = random.Random(0)
+    for _ in range(5):
+        g, h = rng.choice(keys), rng.choice(keys)
+        gh = perm2.Perm2.from_tup(g) * perm2.Perm2.from_tup(h)
+        assert np.allclose(get_mat(g, ydict) @ get_mat(h, ydict), get_mat(gh, ydict))
+    eye = perm2.Perm2.eye(5)
+    assert np.allclose(get_mat(eye, ydict), np.eye(20))
+    # same blocks as the oracle's literal scan, including the cyclic scalars
+    reps = coset_reps(perm2.sn(5), young_subgroup_perm(alpha))
+    o = (1, 0, 2, 2, 1)
+    mine = wreath_rep(o, keys[17], ydict, reps, cyclic_irreps(alpha))
+    assert np.allclose(mine, W.wreath_rep(alpha, parts, o, keys[17]))
+    w = WreathCycSn.from_tup((1, 0, 2, 2, 1), keys[17], 3)
+    assert (w * w.inv()).tup_rep == ((0,) * 5, (1, 2, 3, 4, 5))
+
+
+def test_plancherel_over_all_irreps_of_c3_wr_s4():
+    """sum over all irreps (alpha weak partition of 4 into 3, parts) of D ||f_hat||_F^2 = |G| ||f||^2
+    on the FULL group C_3^4 x S_4 (all 81 orientations)."""
+    n = 4
+    oris = W.orientations(n, zero_sum=False)
+    f = np.random.default_rng(9).standard_normal((24, len(oris)))
+    fd = torch.from_numpy(f).cuda()
+    from snfft_b200.utils import partition_parts, weak_partitions
+    total, dims = 0.0, 0
+    for alpha in weak_partitions(n, 3):
+        for parts in partition_parts(alpha):
+            wp = WreathPlan(alpha, parts, oris=oris)
+            fh = wp.forward(fd)
+            total += wp.D * (fh.abs() ** 2).sum().item()
+            dims += wp.D ** 2
+    assert dims == 24 * 81
+    assert abs(total - 24 * 81 * (f ** 2).sum()) / total < 1e-12
+
+
+@pytest.mark.parametrize('alpha,parts', [((0, 1, 7), ((), (1,), (4, 3))),           # multi.py:177, D = 112
+                                         ((8, 0, 0), ((7, 1), (), ())),             # cube_ft.py:127-128, D = 7
+                                         ((1, 2, 5), ((1,), (1, 1), (3, 2))),       # test_wreath.py:77-78, D = 840
+                                         ((2, 3, 3), ((2,), (1, 1, 1), (1, 1, 1))), # cube_irrep.py:179-180, D = 560
+                                         ((4, 2, 2), ((4,), (2,), (2,)))])          # gen_sparse.py:135-137, D = 420
+def test_cube_irreps_sparse_support(alpha, parts):
+    """BASELINE configs[3]: the 2x2 cube group (3^7 * 8! elements).  f supported on a few group
+    elements: f_hat must equal sum_j c_j rho(g_j) built by the oracle."""
+    wp = WreathPlan(alpha, parts)
+    assert wp.order == 88179840 and len(wp.oris) == 2187
+    rng = np.random.default_rng(38)
+    f = torch.zeros((40320, 2187), dtype=torch.float64, device='cuda')
+    reps, yy = W.coset_reps(8, alpha) if wp.N <= 60 else wp.reps, None
+    want = np.zeros((wp.D, wp.D), dtype=np.complex128)
+    ori_index = {tuple(o): q for q, o in enumerate(wp.oris.tolist())}
+    for _ in range(2 if wp.N > 100 else 4):
+        g = tuple(int(x) + 1 for x in rng.permutation(8))
+        o = tuple(int(x) for x in wp.oris[int(rng.integers(2187))])
+        c = float(rng.standard_normal())
+        f[O.lex_rank(g), ori_index[o]] += c
+        want += c * sparse_rho(wp, alpha, parts, o, g)
+    got = wp.forward(f).cpu().numpy()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-10
+
+
+def sparse_rho(wp, alpha, parts, o, g):
+    """rho(o, g) via the coset of g t_j (same result as the oracle's double scan, checked in
+    test_wreath_yor_homomorphism; the scan needs N^2 products per element)."""
+    index = {t: i for i, t in enumerate(wp.reps)}
+    b = wp.block
+    scal = W.block_cyclic_irreps(alpha, o, wp.reps)
+    mat = np.zeros((wp.D, wp.D), dtype=np.complex128)
+    nz = [(a, p) for a, p in zip(alpha, parts) if a > 0]
+    for j, tj in enumerate(wp.reps):
+        gt = O.perm_mul(g, tj)
+        rep, start = [], 0
+        for a in alpha:
+            rep.extend(sorted(gt[start:start + a]))
+            start += a
+        i = index[tuple(rep)]
+        h = O.perm_mul(O.perm_inv(wp.reps[i]), gt)
+        mats, start = [], 1
+        for a, p in nz:
+            mats.append(O.yor(tuple(p), tuple(x - start + 1 for x in h[start - 1:start - 1 + a])))
+            start += a
+        blk = mats[0]
+        for m in mats[1:]:
+            blk = np.kron(blk, m)
+        mat[i * b:(i + 1) * b, j * b:(j + 1) * b] = scal[i] * blk
+    return mat
