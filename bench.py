@@ -258,16 +258,15 @@ def main():
     hback = torch.empty_like(hx).pin_memory()
 
     def e2e_step():
-        x.copy_(hx, non_blocking=True)
         if sharded:
+            x.copy_(hx, non_blocking=True)
             sp = plan.forward(x)
             hspec.copy_(sp, non_blocking=True)
             hback.copy_(plan.inverse(sp), non_blocking=True)
         else:
-            plan.forward(x, 'coset', out=spec, work=work)
-            hspec.copy_(spec, non_blocking=True)
-            plan.inverse(spec, 'coset', out=back, work=work)
-            hback.copy_(back, non_blocking=True)
+            # public host-buffer entry point: chunks pipelined over several streams so that H2D,
+            # kernels and D2H overlap
+            plan.roundtrip_host(hx, hspec, hback, order='coset', chunks=16, streams=4)
 
     e2e_step()
     barrier()

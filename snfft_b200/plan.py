@@ -197,6 +197,47 @@ class Plan:
                                            self._stream()))
         return out
 
+    def roundtrip_host(self, f_host, fhat_host=None, back_host=None, order: str = "coset",
+                       chunks: int = 8, streams: int = 4):
+        """Forward (and, if ``back_host`` is given, inverse) transform of a batch that lives in
+        pinned host memory: the batch is cut into ``chunks`` pieces that flow through
+        H2D copy -> forward -> D2H copy [-> inverse -> D2H copy] on ``streams`` CUDA streams, so that
+        the PCIe transfers of one piece overlap the kernels and the opposite-direction copies of the
+        others.  f_host / fhat_host / back_host: float64 pinned CPU tensors [batch, n!]."""
+        import torch
+        batch = f_host.shape[0]
+        if f_host.dtype != torch.float64 or f_host.dim() != 2 or f_host.shape[1] != self.size:
+            raise TypeError("f_host must be a float64 CPU tensor [batch, n!]")
+        chunks = max(1, min(chunks, batch))
+        per = (batch + chunks - 1) // chunks
+        dev = f"cuda:{self.device}"
+        key = ("host_pipe", per, streams)
+        if getattr(self, "_pipe_key", None) != key:
+            self._pipe_key = key
+            self._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(streams)]
+            self._pipe_bufs = [[torch.empty((per, self.size), dtype=torch.float64, device=dev) for _ in range(4)]
+                               for _ in range(streams)]
+        start = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(start)
+        for c in range(chunks):
+            lo, hi = c * per, min(batch, (c + 1) * per)
+            if lo >= hi:
+                break
+            st = self._pipe_streams[c % streams]
+            x, spec, back, work = (b[:hi - lo] for b in self._pipe_bufs[c % streams])
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                x.copy_(f_host[lo:hi], non_blocking=True)
+                self.forward(x, order, out=spec, work=work)
+                if fhat_host is not None:
+                    fhat_host[lo:hi].copy_(spec, non_blocking=True)
+                if back_host is not None:
+                    self.inverse(spec, order, out=back, work=work)
+                    back_host[lo:hi].copy_(back, non_blocking=True)
+        for st in self._pipe_streams:
+            start.wait_stream(st)
+
     def unpack(self, packed):
         """{partition: view [..., d, d]} of a packed spectrum, in ``partitions(n)`` order."""
         parts, dims, offs = self.layout()

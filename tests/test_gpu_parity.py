@@ -266,3 +266,16 @@ def test_s9_against_oracle_port():
     ref = O.pack(O.fft_all(f), n)
     got = plan.forward(dev(f), 'lex').cpu().numpy()
     assert per_irrep_err(plan, got, ref) < TOL
+
+
+def test_host_pipeline_matches_device_path():
+    n, B = 7, 37
+    plan = get_plan(n)
+    f = torch.randn(B, 5040, dtype=torch.float64).pin_memory()
+    spec = torch.empty_like(f).pin_memory()
+    back = torch.empty_like(f).pin_memory()
+    plan.roundtrip_host(f, spec, back, order='lex', chunks=5, streams=3)
+    torch.cuda.synchronize()
+    want = plan.forward(f.cuda(), 'lex').cpu()
+    assert torch.equal(spec, want)
+    assert ((back - f).norm() / f.norm()).item() < TOL
