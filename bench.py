@@ -58,7 +58,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
-                 '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                 '-lms', '20', '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                 text=True)
         except Exception:
             self.proc = None
@@ -68,9 +68,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -80,7 +80,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        # samples taken while the GPU was under load (the timed regions), else everything we have
+        inside = [ln for (ts, ln) in self.lines if t0 is not None and t0 <= ts <= t1 + 0.03]
+        in_region = len(inside)
+        for line in (inside if inside else [ln for _, ln in self.lines]):
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 7:
                 continue
@@ -94,7 +97,7 @@ class ClockSampler:
                     reasons.add(name)
         return {'sm_mhz': statistics.median(sm) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'samples_in_timed_region': in_region, 'reasons': sorted(reasons)}
 
 
 def run_reference(args, rank, world):
@@ -141,7 +144,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='s8', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -209,6 +212,7 @@ def main():
     timing_read()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    load_t0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
@@ -218,7 +222,6 @@ def main():
     kinds = timing_read()
     timing_enable(False)
     launches = launch_count() - launches0
-    clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=f'cuda:{local}')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -280,6 +283,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = elements_per_step * args.e2e_steps / (t.item() * 1e-3)
+    clocks = sampler.stop(load_t0, time.time())   # device-timed and end-to-end regions
     assert ((hback - hx).norm() / hx.norm()).item() < 1e-10
 
     cpu = None

@@ -96,3 +96,42 @@ def yor_batch(ferrers, tuples, device=0):
                          device=f'cuda:{device}').reshape(-1, n)
     out = plan.yor(plan.irrep_index(ferrers.partition), perms)
     return out.cpu().numpy()
+
+
+# ---- Young's seminormal form (reference yor.py:119-182); small host-side helper, not on the hot path
+def ysemi_t(f, transposition):
+    """Seminormal matrix of the adjacent transposition (k, k+1): for a tableau t whose swap t' is
+    standard and comes later in the list, rows (t, t') carry [[1/d, 1 - 1/d^2], [1, -1/d]] with d the
+    axial distance; otherwise +1 (same row) or -1 (same column)."""
+    tabs = f.tableaux
+    rep = np.zeros((len(tabs), len(tabs)))
+    i0, i1 = transposition
+    for t in tabs:
+        other = t.transpose(transposition)
+        if other is None:
+            if t.get_row(i0) == t.get_row(i1):
+                rep[t.idx, t.idx] = 1.
+            elif t.get_col(i0) == t.get_col(i1):
+                rep[t.idx, t.idx] = -1.
+            continue
+        if t.idx < other.idx:
+            dist = t.ax_dist(i0, i1)
+            rep[t.idx, t.idx] = 1. / dist
+            rep[t.idx, other.idx] = 1. - 1. / dist ** 2
+            rep[other.idx, t.idx] = 1.
+            rep[other.idx, other.idx] = -1. / dist
+    return rep
+
+
+def ysemi(ferrers, permutation):
+    """Seminormal-form matrix of a permutation: generators along the bubble-sort word of each cycle,
+    accumulated from the left (yor.py:119-146)."""
+    cycles = [c for c in permutation.cycle_decomposition if len(c) > 1]
+    if not cycles:
+        return np.eye(ferrers.n_tabs())
+    res = None
+    for cycle in cycles:
+        for t in reversed(cycle_to_adj_transpositions(cycle, ferrers.size)):
+            y = ysemi_t(ferrers, (min(t), max(t)))
+            res = y if res is None else y.dot(res)
+    return res

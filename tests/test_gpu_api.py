@@ -84,3 +84,22 @@ def test_yor_random_homomorphism_n7():
         g = Perm2.from_tup(tuple(int(x) + 1 for x in rng.permutation(7)))
         h = Perm2.from_tup(tuple(int(x) + 1 for x in rng.permutation(7)))
         assert np.allclose(yor(fd, g) @ yor(fd, h), yor(fd, g * h))
+
+
+def test_sampled_inverse_and_file_job(tmp_path):
+    # tile/par_inv_ft.py:27-45 per state, summed over irreps; s8fft.do_all_ffts from a text table
+    from snfft_b200 import io
+    n = 6
+    values = np.random.default_rng(2).standard_normal(math.factorial(n))
+    spec = sfft.forward(values, n)
+    group = perm2.sn(n)
+    pick = [3, 100, 719, 0]
+    got = sfft.inverse_at(spec, n, [group[i] for i in pick])
+    assert np.allclose(got, values[pick], atol=1e-12)
+    txt = tmp_path / 'table.txt'
+    txt.write_text(''.join('{},{}\n'.format(''.join(map(str, p.tup_rep)), i % 7) for i, p in enumerate(group)))
+    out = io.fft_from_file(str(txt), n, savedir=str(tmp_path / 'fourier'))
+    ref = sfft.forward(np.array([i % 7 for i in range(720)], dtype=np.float64), n)
+    loaded = io.load_fourier(str(tmp_path / 'fourier'), n)
+    for p in partitions(n):
+        assert np.array_equal(out[p], ref[p]) and np.array_equal(loaded[p], ref[p])

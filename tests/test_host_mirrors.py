@@ -134,3 +134,36 @@ def test_no_product_module_imports_the_oracle():
             if name.endswith(('.py', '.cu', '.cpp', '.hpp', '.cuh')):
                 src = open(os.path.join(dirpath, name)).read()
                 assert not re.search(r'^\s*(import|from)\s+(oracle|snfft_oracle)', src, re.M), name
+
+
+def test_ysemi_known_answers():
+    # test.py:53-64
+    from snfft_b200.yor import ysemi
+    ferr = FerrersDiagram((3, 1))
+    p12 = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    p23 = np.array([[0.5, 0.75, 0], [1, -0.5, 0], [0, 0, 1]])
+    p34 = np.array([[1, 0, 0], [0, 1. / 3., 8. / 9.], [0, 1, -1. / 3.]])
+    assert np.allclose(p12, ysemi(ferr, perm2.Perm2({1: 2, 2: 1}, 4)))
+    assert np.allclose(p23, ysemi(ferr, perm2.Perm2({2: 3, 3: 2}, 4)))
+    assert np.allclose(p34, ysemi(ferr, perm2.Perm2({3: 4, 4: 3}, 4)))
+    assert np.allclose(np.eye(3), ysemi(ferr, perm2.Perm2.eye(4)))
+    # a representation: homomorphism on S_4
+    g, h = perm2.Perm2.from_tup((2, 3, 1, 4)), perm2.Perm2.from_tup((1, 4, 3, 2))
+    assert np.allclose(ysemi(ferr, g) @ ysemi(ferr, h), ysemi(ferr, g * h))
+
+
+def test_file_formats(tmp_path):
+    from snfft_b200 import io
+    txt = tmp_path / 'dists.txt'
+    txt.write_text('123,0\n213,1\n321,3\n')
+    perms, vals = io.read_perm_dist(str(txt))
+    assert perms == [(1, 2, 3), (2, 1, 3), (3, 2, 1)] and vals == [0.0, 1.0, 3.0]
+    dense = io.dense_from_perm_dist(perms, vals, 3)
+    assert dense.tolist() == [0.0, 0.0, 1.0, 0.0, 0.0, 3.0]
+    assert io.clean_line('00120,21345,7\n') == ((0, 0, 1, 2, 0), (2, 1, 3, 4, 5), 7)
+    spec = {(3,): np.ones((1, 1)), (2, 1): np.eye(2), (1, 1, 1): -np.ones((1, 1))}
+    io.save_fourier(str(tmp_path / 'fourier'), spec)
+    back = io.load_fourier(str(tmp_path / 'fourier'), 3)
+    assert list(back) == utils.partitions(3) and np.array_equal(back[(2, 1)], np.eye(2))
+    io.save_wreath_fourier(str(tmp_path), (0, 1, 2), ((), (1,), (2,)), np.eye(3, dtype=np.complex128))
+    assert os.path.exists(tmp_path / '(0, 1, 2)' / '((), (1,), (2,)).npy')
