@@ -71,6 +71,8 @@ struct snfft_plan {
   int ntiles[kMaxN + 1] = {};
   size_t level_smem[kMaxN + 1] = {};
   FusedDev fused;
+  std::vector<PhaseDev> phase_dev[kMaxN + 1];  // row-group phases of levels >= 9
+  P1Dev p1_dev[kMaxN + 1] = {};                // generated in-place stages 1..4 of levels >= 9
   uint32_t* lex_table = nullptr;
   std::mutex lazy_mu;
   std::map<int, YorTables> yor_tables;
@@ -187,6 +189,90 @@ void upload_level(snfft_plan* plan, int k) {
   plan->tiles_dev[k] = plan->upload(tiles);
 }
 
+void upload_phases(snfft_plan* plan, int k) {
+  const LevelProgram& prog = plan->host.programs[k];
+  if (prog.panels.empty() || prog.panels[0].phases.empty()) return;
+  const size_t nphases = prog.panels[0].phases.size();
+  for (size_t ph = 0; ph < nphases; ++ph) {
+    std::vector<PhasePanelDev> panels;
+    std::vector<PhaseGroup> groups;
+    std::vector<PhaseRow> rows;
+    std::vector<PhaseBlock> blocks;
+    int64_t items = 0;
+    int max_rows = 1;
+    for (const PanelProgram& P : prog.panels) {
+      const PanelPhase& pp = P.phases[ph];
+      PhasePanelDev pd;
+      pd.d = P.d;
+      pd.tiles = (P.d + 31) / 32;
+      pd.grp_off = (int32_t)groups.size();
+      pd.ngroups = (int32_t)pp.groups.size();
+      pd.item_off = items;
+      items += (int64_t)pd.ngroups * pd.tiles;
+      panels.push_back(pd);
+      for (PhaseGroup g : pp.groups) {
+        g.row_off += (uint32_t)rows.size();
+        g.blk_off += (uint32_t)blocks.size();
+        groups.push_back(g);
+      }
+      rows.insert(rows.end(), pp.rows.begin(), pp.rows.end());
+      blocks.insert(blocks.end(), pp.blocks.begin(), pp.blocks.end());
+      max_rows = std::max(max_rows, pp.max_rows);
+    }
+    PhaseDev D;
+    D.panels = plan->upload(panels);
+    D.groups = plan->upload(groups);
+    D.rows = plan->upload(rows);
+    D.blocks = plan->upload(blocks);
+    D.coef = plan->level_dev[k].coef;
+    D.nitems = items;
+    D.in_stride = plan->host.fact[k];
+    D.out_stride = plan->host.fact[k];
+    D.npanels = (int32_t)panels.size();
+    D.max_rows = max_rows;
+    plan->phase_dev[k].push_back(D);
+  }
+}
+
+void upload_p1(snfft_plan* plan, int k) {
+  const LevelProgram& prog = plan->host.programs[k];
+  std::vector<P1Entry> entries;
+  std::vector<P0Row> rows;
+  for (const PanelProgram& P : prog.panels) {
+    for (int cw = 0; cw < P.d; ++cw)
+      if (P.chain_base[cw] == cw)
+        entries.push_back(P1Entry{P.chain_sigma[cw], P.d, (int64_t)P.in_off + (int64_t)cw * P.d, 0});
+    // rows whose last writer is a block of stages 1..4
+    std::vector<int> last(P.k * P.d, -1);
+    for (size_t b = 0; b < P.blocks.size(); ++b)
+      for (int a = 0; a < P.blocks[b].m; ++a) last[P.blocks[b].slot[a]] = (int)b;
+    for (int s = 0; s < P.k * P.d; ++s)
+      if (last[s] < 4 * P.d)
+        rows.push_back(P0Row{P.rowbase[s], P.dest[s], P.d, 0, P.fscale[s], P.fscale[s] * P.weight[s], 0});
+  }
+  std::stable_sort(entries.begin(), entries.end(), [](const P1Entry& a, const P1Entry& b) { return a.sigma < b.sigma; });
+  int64_t items = 0;
+  for (P1Entry& e : entries) {
+    e.item_off = items;
+    items += (e.d + 31) / 32;
+  }
+  int64_t row_items = 0;
+  for (P0Row& r : rows) {
+    r.item_off = row_items;
+    row_items += (r.d + 31) / 32;
+  }
+  P1Dev& D = plan->p1_dev[k];
+  D.entries = plan->upload(entries);
+  D.rows = plan->upload(rows);
+  D.nitems = items;
+  D.nrow_items = row_items;
+  D.in_stride = plan->host.fact[k];
+  D.out_stride = plan->host.fact[k];
+  D.rI = plan->host.fact[k - 1];
+  D.nentries = (int32_t)entries.size();
+  D.nrows = (int32_t)rows.size();
+}
+
 template <class F>
 int guarded(F&& f) {
   try {
@@ -220,6 +306,20 @@ const ShapeInfo& shape_of(const snfft_plan* plan, int k, int irrep) {
   if (k < 1 || k > plan->host.n) throw InvalidArg("k out of range");
   if (irrep < 0 || irrep >= (int)plan->host.levels[k].shapes.size()) throw InvalidArg("irrep out of range");
   return plan->host.levels[k].shapes[irrep];
+}
+
+// Levels >= 9 inside snfft_forward / snfft_inverse: row-group phases.  xside = the buffer holding
+// the k sub-spectra per group (forward: the level's input, overwritten with intermediate rows;
+// inverse: the level's output), sside = the packed spectra of the level.
+void run_level_phases(const snfft_plan* plan, int k, double* xside, double* sside, int64_t groups,
+                      bool inverse, cudaStream_t stream) {
+  const std::vector<PhaseDev>& phases = plan->phase_dev[k];
+  const int np = (int)phases.size();
+  // phase 0 (stages 1..4) runs as generated in-place register programs, the others table-driven
+  if (!inverse) CUDA_OK(launch_p1_inplace(plan->p1_dev[k], xside, sside, groups, false, plan->num_sms, stream));
+  for (int i = 1; i < np; ++i)
+    CUDA_OK(launch_phase(phases[inverse ? np - i : i], xside, sside, groups, inverse, plan->num_sms, stream));
+  if (inverse) CUDA_OK(launch_p1_inplace(plan->p1_dev[k], xside, sside, groups, true, plan->num_sms, stream));
 }
 
 void run_level(const snfft_plan* plan, int k, const double* in, double* out, int64_t groups,
@@ -412,6 +512,10 @@ int snfft_plan_create(int n, int device, snfft_plan** out) {
       plan->num_sms = prop.multiProcessorCount;
       CUDA_OK(prepare_kernels());
       for (int k = 2; k <= n; ++k) upload_level(plan, k);
+      for (int k = kPhaseMinLevel; k <= n; ++k) {
+        upload_phases(plan, k);
+        upload_p1(plan, k);
+      }
       for (int k = 2; k <= std::min(n, kFusedMax); ++k) plan->fused.level[k] = plan->level_dev[k];
       if (n <= 10) {
         plan->lex_table = (uint32_t*)plan->alloc((size_t)plan->host.fact[n] * sizeof(uint32_t));
@@ -529,7 +633,11 @@ int snfft_forward(const snfft_plan* plan, const double* f_dev, double* fhat_dev,
     }
     for (int k = k0 + 1; k <= n; ++k) {
       double* nxt = out_of(pass++);
-      run_level(plan, k, cur, nxt, batch * (nf / plan->host.fact[k]), false, stream);
+      const int64_t groups = batch * (nf / plan->host.fact[k]);
+      if (!plan->phase_dev[k].empty() && !g_force_table_driven && cur != f_dev)
+        run_level_phases(plan, k, const_cast<double*>(cur), nxt, groups, false, stream);  // cur is scratch
+      else
+        run_level(plan, k, cur, nxt, groups, false, stream);
       cur = nxt;
     }
   });
@@ -565,7 +673,11 @@ int snfft_inverse(const snfft_plan* plan, const double* fhat_dev, double* f_dev,
     int pass = 0;
     for (int k = n; k > k0; --k) {
       double* nxt = out_of(pass++);
-      run_level(plan, k, cur, nxt, batch * (nf / plan->host.fact[k]), true, stream);
+      const int64_t groups = batch * (nf / plan->host.fact[k]);
+      if (!plan->phase_dev[k].empty() && !g_force_table_driven)
+        run_level_phases(plan, k, nxt, const_cast<double*>(cur), groups, true, stream);  // cur is only read
+      else
+        run_level(plan, k, cur, nxt, groups, true, stream);
       cur = nxt;
     }
     if (k0 >= 4) {

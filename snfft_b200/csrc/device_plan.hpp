@@ -42,6 +42,53 @@ struct Tile {
   int32_t cap;
 };
 
+// Row-group phase of a level (levels >= 9): see plan.hpp
+struct PhasePanelDev {
+  int32_t d;         // columns of the panel
+  int32_t tiles;     // ceil(d / 32)
+  int32_t grp_off;   // first group in PhaseDev::groups
+  int32_t ngroups;
+  int64_t item_off;  // prefix sum of ngroups * tiles
+};
+
+struct PhaseDev {
+  const PhasePanelDev* panels;
+  const PhaseGroup* groups;  // row_off / blk_off are absolute here
+  const PhaseRow* rows;
+  const PhaseBlock* blocks;
+  const double* coef;
+  int64_t nitems;
+  int64_t in_stride, out_stride;  // group strides of the X-side and spectrum-side buffers
+  int32_t npanels;
+  int32_t max_rows;
+};
+
+// In-place phase 1 of a large level as generated register programs: one entry per (panel, upper
+// chain down to W^5); rows (i, t), i < 5, t < d_sigma at base + i * (k-1)! + t * d.
+struct P1Entry {
+  int32_t sigma;     // program (shape of W^5)
+  int32_t d;         // columns and row pitch of the panel
+  int64_t base;      // in_off + ubase * d
+  int64_t item_off;  // prefix sum of ceil(d / 32) over the entries
+};
+// A row that is finished after stage 4: forward out[dest] = scale_f * x[xoff]; inverse
+// x[xoff] = scale_i * out[dest].
+struct P0Row {
+  uint32_t xoff, dest;
+  int32_t d;
+  int32_t pad;
+  double scale_f, scale_i;
+  int64_t item_off;
+};
+struct P1Dev {
+  const P1Entry* entries;
+  const P0Row* rows;
+  int64_t nitems, nrow_items;
+  int64_t in_stride, out_stride;
+  int64_t rI;  // (k-1)!
+  int32_t nentries, nrows;
+};
+
 constexpr int kFusedMax = 7;  // 2 * 7! doubles = 80,640 B of shared memory
 
 struct FusedDev {

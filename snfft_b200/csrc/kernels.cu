@@ -519,6 +519,106 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// row-group phase kernel (levels >= 9).  One warp = one (row group, 32-column tile): the lanes own
+// one column each, the group's rows sit in a lane-private shared-memory column, the group's blocks
+// run back to back (uniform control flow, no barriers), rows go back with coalesced 256-byte runs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPhaseWarps = 8;
+
+template <bool INV>
+__global__ void __launch_bounds__(kPhaseWarps * 32)
+phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside, int64_t lgroups) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* col = sm + (size_t)warp * P.max_rows * 32 + lane;
+  for (int64_t item = (int64_t)blockIdx.x * kPhaseWarps + warp; item < P.nitems;
+       item += (int64_t)gridDim.x * kPhaseWarps) {
+    int pi = 0;
+    while (pi + 1 < P.npanels && item >= P.panels[pi + 1].item_off) ++pi;
+    const PhasePanelDev pan = P.panels[pi];
+    const int64_t rem = item - pan.item_off;
+    const int group = (int)(rem / pan.tiles), tile = (int)(rem - (int64_t)group * pan.tiles);
+    const int c = tile * 32 + lane;
+    const bool active = c < pan.d;
+    const PhaseGroup G = P.groups[pan.grp_off + group];
+    const PhaseRow* __restrict__ rows = P.rows + G.row_off;
+    const PhaseBlock* __restrict__ blocks = P.blocks + G.blk_off;
+    for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
+      double* xs = xside + lg * P.in_stride + c;
+      double* ss = sside + lg * P.out_stride + c;
+      if (active) {
+        for (int r = 0; r < G.nrows; ++r) {
+          const PhaseRow row = rows[r];
+          col[r * 32] = (INV && row.final) ? ss[row.dest] : xs[row.xoff];
+        }
+        for (int bi = 0; bi < G.nblk; ++bi) {
+          const PhaseBlock b = blocks[INV ? G.nblk - 1 - bi : bi];
+          double x[kMaxBlock], y[kMaxBlock];
+#pragma unroll
+          for (int i = 0; i < kMaxBlock; ++i)
+            if (i < b.m) x[i] = col[b.loc[i] * 32];
+          matvec_m(b.m, P.coef + (INV ? b.coef_i : b.coef_f), x, y);
+#pragma unroll
+          for (int i = 0; i < kMaxBlock; ++i)
+            if (i < b.m) col[b.loc[i] * 32] = y[i];
+        }
+        for (int r = 0; r < G.nrows; ++r) {
+          const PhaseRow row = rows[r];
+          if (!INV && row.final)
+            ss[row.dest] = col[r * 32];
+          else
+            xs[row.xoff] = col[r * 32];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stages 1..4 of a large level (k >= 9) as generated in-place register programs: one warp = one
+// (upper chain, 32-column tile), lanes = columns; plus the scaled row move of finished rows.
+// ---------------------------------------------------------------------------------------------
+template <bool INV>
+__global__ void __launch_bounds__(256)
+p1_inplace_kernel(P1Dev P, double* __restrict__ xside, int64_t lgroups) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < P.nitems; item += (int64_t)gridDim.x * 8) {
+    // entries are sorted by sigma and item_off is increasing: binary search
+    int lo = 0, hi = P.nentries - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (P.entries[mid].item_off <= item) lo = mid; else hi = mid - 1;
+    }
+    const P1Entry e = P.entries[lo];
+    const int c = (int)(item - e.item_off) * 32 + lane;
+    if (c >= e.d) continue;
+    for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y)
+      gen::p1ip_run<INV>(e.sigma, xside + lg * P.in_stride + e.base + c, P.rI, e.d);
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(256)
+p0_rows_kernel(P1Dev P, double* __restrict__ xside, double* __restrict__ sside, int64_t lgroups) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < P.nrow_items; item += (int64_t)gridDim.x * 8) {
+    int lo = 0, hi = P.nrows - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (P.rows[mid].item_off <= item) lo = mid; else hi = mid - 1;
+    }
+    const P0Row r = P.rows[lo];
+    const int c = (int)(item - r.item_off) * 32 + lane;
+    if (c >= r.d) continue;
+    for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
+      double* xs = xside + lg * P.in_stride + r.xoff + c;
+      double* ss = sside + lg * P.out_stride + r.dest + c;
+      if (!INV) *ss = r.scale_f * *xs; else *xs = r.scale_i * *ss;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // element order
 // ---------------------------------------------------------------------------------------------
 struct Facts {
@@ -714,6 +814,8 @@ cudaError_t prepare_kernels() {
   cudaError_t e;
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
@@ -791,6 +893,59 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
   else
     fused_kernel<K0, false><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
   return cudaGetLastError();
+}
+
+cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
+                         int num_sms, cudaStream_t stream) {
+  if (lgroups <= 0 || P.nitems <= 0) return cudaSuccess;
+  const size_t smem = (size_t)kPhaseWarps * P.max_rows * 32 * sizeof(double);
+  int64_t gy = lgroups < 64 ? lgroups : 64;
+  int64_t gx = (P.nitems + kPhaseWarps - 1) / kPhaseWarps;
+  const int64_t want = 16LL * num_sms;  // enough CTAs to fill the machine; the rest is grid-stride
+  if (gx * gy > want) gx = (want + gy - 1) / gy;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+  if (inverse)
+    phase_kernel<true><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+  else
+    phase_kernel<false><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
+                              int num_sms, cudaStream_t stream) {
+  if (lgroups <= 0) return cudaSuccess;
+  auto grid_for = [&](int64_t items) {
+    int64_t gy = lgroups < 64 ? lgroups : 64;
+    int64_t gx = (items + 7) / 8;
+    const int64_t want = 32LL * num_sms;
+    if (gx * gy > want) gx = (want + gy - 1) / gy;
+    if (gx < 1) gx = 1;
+    return dim3((unsigned)gx, (unsigned)gy);
+  };
+  // forward: programs, then move the finished rows out; inverse: bring them in (scaled) first
+  for (int step = 0; step < 2; ++step) {
+    const bool rows_pass = inverse ? step == 0 : step == 1;
+    if (rows_pass) {
+      if (P.nrow_items <= 0) continue;
+      LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+      if (inverse)
+        p0_rows_kernel<true><<<grid_for(P.nrow_items), 256, 0, stream>>>(P, xside, sside, lgroups);
+      else
+        p0_rows_kernel<false><<<grid_for(P.nrow_items), 256, 0, stream>>>(P, xside, sside, lgroups);
+    } else {
+      if (P.nitems <= 0) continue;
+      LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+      if (inverse)
+        p1_inplace_kernel<true><<<grid_for(P.nitems), 256, 0, stream>>>(P, xside, lgroups);
+      else
+        p1_inplace_kernel<false><<<grid_for(P.nitems), 256, 0, stream>>>(P, xside, lgroups);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_fused(const FusedDev& F, const double* in, double* out, int64_t groups,

@@ -22,6 +22,16 @@ cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, s
                          const double* in, double* out, int64_t groups, bool inverse, int num_sms,
                          cudaStream_t stream);
 
+// One row-group phase of a level: xside holds the in-place rows (input of the level, clobbered by
+// the forward direction; output of the level in the inverse direction), sside the finished rows.
+cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
+                         int num_sms, cudaStream_t stream);
+
+// Stages 1..4 of a large level as in-place generated programs plus the pass that moves the rows
+// finished after stage 4 to / from the spectrum-side buffer.
+cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
+                              int num_sms, cudaStream_t stream);
+
 // Fused low levels 2..k0 of `groups` independent S_{k0} blocks, entirely in shared memory.
 cudaError_t launch_fused(const FusedDev& F, const double* in, double* out, int64_t groups,
                          bool inverse, int num_sms, cudaStream_t stream);

@@ -320,6 +320,92 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
   }
 }
 
+
+// Cut the stages of a panel into phases and its rows into groups closed under each phase.
+void build_phases(PanelProgram& P) {
+  const int k = P.k, d = P.d, rows = k * d;
+  // stage ranges: [1..4] then chunks of up to 4 stages, the last two chunks balanced
+  std::vector<std::pair<int, int>> ranges;
+  ranges.push_back({1, std::min(4, k - 1)});
+  int lo = 5;
+  while (lo <= k - 1) {
+    const int left = k - lo;  // stages lo..k-1
+    int len = left <= 4 ? left : (left <= 6 ? (left + 1) / 2 : 4);
+    ranges.push_back({lo, lo + len - 1});
+    lo += len;
+  }
+  std::vector<int> last_writer(rows, -1);
+  for (size_t b = 0; b < P.blocks.size(); ++b)
+    for (int a = 0; a < P.blocks[b].m; ++a) last_writer[P.blocks[b].slot[a]] = (int)b;
+  for (auto& rg : ranges) {
+    PanelPhase ph;
+    ph.stage_lo = rg.first;
+    ph.stage_hi = rg.second;
+    const int b0 = (rg.first - 1) * d, b1 = rg.second * d;  // blocks of these stages
+    std::vector<int> parent(rows);
+    for (int i = 0; i < rows; ++i) parent[i] = i;
+    auto find = [&](int x) {
+      while (parent[x] != x) {
+        parent[x] = parent[parent[x]];
+        x = parent[x];
+      }
+      return x;
+    };
+    std::vector<char> touched(rows, 0);
+    for (int b = b0; b < b1; ++b) {
+      const Block& blk = P.blocks[b];
+      const int r0 = find(blk.slot[0]);
+      touched[blk.slot[0]] = 1;
+      for (int a = 1; a < blk.m; ++a) {
+        touched[blk.slot[a]] = 1;
+        const int ra = find(blk.slot[a]);
+        if (ra != r0) parent[ra] = r0;
+      }
+    }
+    // group id per root, rows in slot order, blocks in stage order
+    std::vector<int> gid(rows, -1);
+    std::vector<std::vector<int>> grows, gblocks;
+    for (int s = 0; s < rows; ++s) {
+      if (!touched[s]) continue;
+      const int r = find(s);
+      if (gid[r] < 0) {
+        gid[r] = (int)grows.size();
+        grows.emplace_back();
+        gblocks.emplace_back();
+      }
+      grows[gid[r]].push_back(s);
+    }
+    for (int b = b0; b < b1; ++b) gblocks[gid[find(P.blocks[b].slot[0])]].push_back(b);
+    std::vector<int> local(rows, -1);
+    for (size_t g = 0; g < grows.size(); ++g) {
+      if ((int)grows[g].size() > kPhaseMaxRows) throw std::runtime_error("phase group too large");
+      PhaseGroup G;
+      G.row_off = (uint32_t)ph.rows.size();
+      G.blk_off = (uint32_t)ph.blocks.size();
+      G.nrows = (uint16_t)grows[g].size();
+      G.nblk = (uint16_t)gblocks[g].size();
+      ph.max_rows = std::max<int>(ph.max_rows, G.nrows);
+      for (size_t q = 0; q < grows[g].size(); ++q) {
+        const int s = grows[g][q];
+        local[s] = (int)q;
+        const bool fin = last_writer[s] >= b0 && last_writer[s] < b1;
+        ph.rows.push_back(PhaseRow{P.rowbase[s], P.dest[s], fin ? 1u : 0u});
+      }
+      for (int b : gblocks[g]) {
+        const Block& blk = P.blocks[b];
+        PhaseBlock pb{};
+        pb.m = blk.m;
+        for (int a = 0; a < blk.m; ++a) pb.loc[a] = (uint8_t)local[blk.slot[a]];
+        pb.coef_f = blk.coef_f;
+        pb.coef_i = blk.coef_i;
+        ph.blocks.push_back(pb);
+      }
+      ph.groups.push_back(G);
+    }
+    P.phases.push_back(std::move(ph));
+  }
+}
+
 }  // namespace
 
 void build_host_plan(int n, HostPlan& plan) {
@@ -390,7 +476,10 @@ void build_host_plan(int n, HostPlan& plan) {
     const int np = (int)plan.levels[k - 1].shapes.size();
     L.panels.resize(np);
     std::map<std::vector<double>, uint32_t> coef_index;
-    for (int mu = 0; mu < np; ++mu) build_panel(plan, k, mu, L, coef_index, L.panels[mu]);
+    for (int mu = 0; mu < np; ++mu) {
+      build_panel(plan, k, mu, L, coef_index, L.panels[mu]);
+      if (k >= kPhaseMinLevel) build_phases(L.panels[mu]);
+    }
   }
 }
 

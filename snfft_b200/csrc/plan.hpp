@@ -50,6 +50,35 @@ struct alignas(16) Block {
 };
 static_assert(sizeof(Block) == 32, "Block must be 32 bytes");
 
+// ---- row-group phases (levels >= 9) -------------------------------------------------------------
+// The k-1 stages of a level are cut into a few consecutive ranges ("phases").  Inside one phase the
+// rows of a panel fall into small groups that are closed under the phase's blocks (connected
+// components of "block touches row"; <= 48 rows for n <= 12), so a warp can load one group for 32
+// columns, run all its blocks and store it back: one coalesced pass over HBM per phase.
+struct PhaseRow {
+  uint32_t xoff;   // offset of the row in the X-side buffer (its in-place slot), start of the run
+  uint32_t dest;   // offset of the finished row in the spectrum-side buffer
+  uint32_t final;  // 1: the row is finished in this phase (forward: store to dest; inverse: load from dest)
+};
+struct PhaseBlock {
+  uint8_t loc[kMaxBlock];  // rows of the block, as indices into the group's row list
+  uint8_t m;
+  uint8_t pad[2];
+  uint32_t coef_f, coef_i;
+};
+static_assert(sizeof(PhaseBlock) == 16, "PhaseBlock must be 16 bytes");
+struct PhaseGroup {
+  uint32_t row_off, blk_off;  // into the level's row / block arrays of this phase
+  uint16_t nrows, nblk;
+};
+struct PanelPhase {
+  int stage_lo = 0, stage_hi = 0;  // stages [lo, hi], 1-based
+  std::vector<PhaseGroup> groups;  // row_off / blk_off relative to this panel's vectors
+  std::vector<PhaseRow> rows;
+  std::vector<PhaseBlock> blocks;
+  int max_rows = 0;
+};
+
 // Program of one column block mu |- k-1 of level k: k*d rows ("slots"), k-1 stages of d blocks.
 struct PanelProgram {
   int k = 0, mu = 0;
@@ -58,6 +87,7 @@ struct PanelProgram {
   std::vector<Block> blocks;       // stage-major: stage s (1..k-1) is blocks[(s-1)*d, s*d)
   std::vector<uint32_t> dest;      // slot -> offset in the k! output (start of a run of d)
   std::vector<uint32_t> rowbase;   // slot -> offset in the k! input (start of a run of d)
+  std::vector<PanelPhase> phases;  // k >= 9 only
   // ---- host-only metadata for the code generator (gen_programs.cpp) ----
   std::vector<uint32_t> coef_raw;  // per block: forward matrix before the final scales are folded in
   std::vector<int32_t> block_chain;  // per block: index of its chain W in tab(mu)
@@ -94,6 +124,9 @@ struct HostPlan {
 
 // Throws std::runtime_error on invalid n.
 void build_host_plan(int n, HostPlan& plan);
+
+constexpr int kPhaseMinLevel = 9;   // levels >= 9 run as row-group phases
+constexpr int kPhaseMaxRows = 64;   // rows of a group (shared-memory tile of a warp: rows x 32 columns)
 
 // Dense rho_lambda((j j+1)) for shape `irrep` of level k (row-major d*d), from lattice chains.
 void yor_trans_dense(const HostPlan& plan, int k, int irrep, int j, double* out);
