@@ -152,6 +152,11 @@ int snfft_shard_columns(const snfft_shard* shard, int r, int k, int irrep, int32
  * out double[groups][size(k)] (inverse != 0: the other way). */
 int snfft_shard_level(const snfft_shard* shard, int k, const double* in_dev, double* out_dev,
                       int64_t groups, int inverse, void* stream);
+/* Same level with explicit roles: x_dev holds the k sub-spectra per group (size k * size(k-1)), s_dev
+ * the spectra (size(k)).  Forward reads x_dev and MAY OVERWRITE it with intermediate rows (levels
+ * >= 9 run as in-place row-group phases), writing s_dev; inverse reads s_dev and writes x_dev. */
+int snfft_shard_level_scratch(const snfft_shard* shard, int k, double* x_dev, double* s_dev,
+                              int64_t groups, int inverse, void* stream);
 /* Host export of the shard tables of one panel of level k (CPU tests): owned width, per-slot
  * destination / input offsets in the compact layouts, and the group strides.  The blocks and
  * coefficients are those of snfft_export_panel. */

@@ -189,8 +189,18 @@ void upload_level(snfft_plan* plan, int k) {
   plan->tiles_dev[k] = plan->upload(tiles);
 }
 
-void upload_phases(snfft_plan* plan, int k) {
-  const LevelProgram& prog = plan->host.programs[k];
+// Layout of one level as seen by the phase kernels: the whole transform (offsets of the plan) or a
+// column shard (per-rank compact offsets).
+struct LevelLayout {
+  std::vector<int> width;                                  // columns of every panel
+  std::vector<const uint32_t*> rowbase, dest;              // per panel: slot -> offset
+  std::vector<int64_t> panel_off;                          // per panel: offset of the panel in a sub-spectrum
+  int64_t in_stride = 0, out_stride = 0, block_stride = 0;  // group strides, distance between X_i blocks
+};
+
+template <class Uploader>
+void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const double* coef, Uploader&& up,
+                      std::vector<PhaseDev>& out_devs) {
   if (prog.panels.empty() || prog.panels[0].phases.empty()) return;
   const size_t nphases = prog.panels[0].phases.size();
   for (size_t ph = 0; ph < nphases; ++ph) {
@@ -200,55 +210,64 @@ void upload_phases(snfft_plan* plan, int k) {
     std::vector<PhaseBlock> blocks;
     int64_t items = 0;
     int max_rows = 1;
-    for (const PanelProgram& P : prog.panels) {
+    for (size_t p = 0; p < prog.panels.size(); ++p) {
+      const PanelProgram& P = prog.panels[p];
       const PanelPhase& pp = P.phases[ph];
+      const int w = lay.width[p];
       PhasePanelDev pd;
-      pd.d = P.d;
-      pd.tiles = (P.d + 31) / 32;
+      pd.d = w;
+      pd.tiles = (w + 31) / 32;
       pd.grp_off = (int32_t)groups.size();
-      pd.ngroups = (int32_t)pp.groups.size();
+      pd.ngroups = w > 0 ? (int32_t)pp.groups.size() : 0;
       pd.item_off = items;
       items += (int64_t)pd.ngroups * pd.tiles;
       panels.push_back(pd);
+      if (w == 0) continue;
       for (PhaseGroup g : pp.groups) {
         g.row_off += (uint32_t)rows.size();
         g.blk_off += (uint32_t)blocks.size();
         groups.push_back(g);
       }
-      rows.insert(rows.end(), pp.rows.begin(), pp.rows.end());
+      for (size_t r = 0; r < pp.rows.size(); ++r) {
+        const uint32_t slot = pp.row_slot[r];
+        rows.push_back(PhaseRow{lay.rowbase[p][slot], lay.dest[p][slot], pp.rows[r].final});
+      }
       blocks.insert(blocks.end(), pp.blocks.begin(), pp.blocks.end());
       max_rows = std::max(max_rows, pp.max_rows);
     }
     PhaseDev D;
-    D.panels = plan->upload(panels);
-    D.groups = plan->upload(groups);
-    D.rows = plan->upload(rows);
-    D.blocks = plan->upload(blocks);
-    D.coef = plan->level_dev[k].coef;
+    D.panels = up(panels);
+    D.groups = up(groups);
+    D.rows = up(rows);
+    D.blocks = up(blocks);
+    D.coef = coef;
     D.nitems = items;
-    D.in_stride = plan->host.fact[k];
-    D.out_stride = plan->host.fact[k];
+    D.in_stride = lay.in_stride;
+    D.out_stride = lay.out_stride;
     D.npanels = (int32_t)panels.size();
     D.max_rows = max_rows;
-    plan->phase_dev[k].push_back(D);
+    out_devs.push_back(D);
   }
 }
 
-void upload_p1(snfft_plan* plan, int k) {
-  const LevelProgram& prog = plan->host.programs[k];
+template <class Uploader>
+void build_p1_dev(const LevelProgram& prog, const LevelLayout& lay, Uploader&& up, P1Dev& D) {
   std::vector<P1Entry> entries;
   std::vector<P0Row> rows;
-  for (const PanelProgram& P : prog.panels) {
+  for (size_t p = 0; p < prog.panels.size(); ++p) {
+    const PanelProgram& P = prog.panels[p];
+    const int w = lay.width[p];
+    if (w == 0) continue;
     for (int cw = 0; cw < P.d; ++cw)
       if (P.chain_base[cw] == cw)
-        entries.push_back(P1Entry{P.chain_sigma[cw], P.d, (int64_t)P.in_off + (int64_t)cw * P.d, 0});
+        entries.push_back(P1Entry{P.chain_sigma[cw], w, lay.panel_off[p] + (int64_t)cw * w, 0});
     // rows whose last writer is a block of stages 1..4
     std::vector<int> last(P.k * P.d, -1);
     for (size_t b = 0; b < P.blocks.size(); ++b)
       for (int a = 0; a < P.blocks[b].m; ++a) last[P.blocks[b].slot[a]] = (int)b;
     for (int s = 0; s < P.k * P.d; ++s)
       if (last[s] < 4 * P.d)
-        rows.push_back(P0Row{P.rowbase[s], P.dest[s], P.d, 0, P.fscale[s], P.fscale[s] * P.weight[s], 0});
+        rows.push_back(P0Row{lay.rowbase[p][s], lay.dest[p][s], w, 0, P.fscale[s], P.fscale[s] * P.weight[s], 0});
   }
   std::stable_sort(entries.begin(), entries.end(), [](const P1Entry& a, const P1Entry& b) { return a.sigma < b.sigma; });
   int64_t items = 0;
@@ -261,16 +280,41 @@ void upload_p1(snfft_plan* plan, int k) {
     r.item_off = row_items;
     row_items += (r.d + 31) / 32;
   }
-  P1Dev& D = plan->p1_dev[k];
-  D.entries = plan->upload(entries);
-  D.rows = plan->upload(rows);
+  D.entries = up(entries);
+  D.rows = up(rows);
   D.nitems = items;
   D.nrow_items = row_items;
-  D.in_stride = plan->host.fact[k];
-  D.out_stride = plan->host.fact[k];
-  D.rI = plan->host.fact[k - 1];
+  D.in_stride = lay.in_stride;
+  D.out_stride = lay.out_stride;
+  D.rI = lay.block_stride;
   D.nentries = (int32_t)entries.size();
   D.nrows = (int32_t)rows.size();
+}
+
+LevelLayout plain_layout(const snfft_plan* plan, int k) {
+  const LevelProgram& prog = plan->host.programs[k];
+  LevelLayout lay;
+  for (const PanelProgram& P : prog.panels) {
+    lay.width.push_back(P.d);
+    lay.rowbase.push_back(P.rowbase.data());
+    lay.dest.push_back(P.dest.data());
+    lay.panel_off.push_back(P.in_off);
+  }
+  lay.in_stride = lay.out_stride = plan->host.fact[k];
+  lay.block_stride = plan->host.fact[k - 1];
+  return lay;
+}
+
+void upload_phases(snfft_plan* plan, int k) {
+  const LevelLayout lay = plain_layout(plan, k);
+  auto up = [&](const auto& v) { return plan->upload(v); };
+  build_phase_devs(plan->host.programs[k], lay, plan->level_dev[k].coef, up, plan->phase_dev[k]);
+}
+
+void upload_p1(snfft_plan* plan, int k) {
+  const LevelLayout lay = plain_layout(plan, k);
+  auto up = [&](const auto& v) { return plan->upload(v); };
+  build_p1_dev(plan->host.programs[k], lay, up, plan->p1_dev[k]);
 }
 
 template <class F>
@@ -311,15 +355,22 @@ const ShapeInfo& shape_of(const snfft_plan* plan, int k, int irrep) {
 // Levels >= 9 inside snfft_forward / snfft_inverse: row-group phases.  xside = the buffer holding
 // the k sub-spectra per group (forward: the level's input, overwritten with intermediate rows;
 // inverse: the level's output), sside = the packed spectra of the level.
+void run_phases(const std::vector<PhaseDev>& phases, const P1Dev& p1, int num_sms, double* xside,
+                double* sside, int64_t groups, bool inverse, cudaStream_t stream);
+
 void run_level_phases(const snfft_plan* plan, int k, double* xside, double* sside, int64_t groups,
                       bool inverse, cudaStream_t stream) {
-  const std::vector<PhaseDev>& phases = plan->phase_dev[k];
+  run_phases(plan->phase_dev[k], plan->p1_dev[k], plan->num_sms, xside, sside, groups, inverse, stream);
+}
+
+void run_phases(const std::vector<PhaseDev>& phases, const P1Dev& p1, int num_sms, double* xside,
+                double* sside, int64_t groups, bool inverse, cudaStream_t stream) {
   const int np = (int)phases.size();
   // phase 0 (stages 1..4) runs as generated in-place register programs, the others table-driven
-  if (!inverse) CUDA_OK(launch_p1_inplace(plan->p1_dev[k], xside, sside, groups, false, plan->num_sms, stream));
+  if (!inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, false, num_sms, stream));
   for (int i = 1; i < np; ++i)
-    CUDA_OK(launch_phase(phases[inverse ? np - i : i], xside, sside, groups, inverse, plan->num_sms, stream));
-  if (inverse) CUDA_OK(launch_p1_inplace(plan->p1_dev[k], xside, sside, groups, true, plan->num_sms, stream));
+    CUDA_OK(launch_phase(phases[inverse ? np - i : i], xside, sside, groups, inverse, num_sms, stream));
+  if (inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, true, num_sms, stream));
 }
 
 void run_level(const snfft_plan* plan, int k, const double* in, double* out, int64_t groups,
@@ -364,6 +415,8 @@ struct ShardLevel {
   Tile* tiles_dev = nullptr;
   int ntiles = 0;
   size_t smem = 0;
+  std::vector<PhaseDev> phases;  // k >= 9: row-group phases on the shard's compact layout
+  P1Dev p1 = {};
 };
 
 struct snfft_shard {
@@ -476,6 +529,21 @@ void build_shard_level(snfft_shard* sh, int k) {
   plan_tiles(prog, SL.width, tiles, SL.smem);
   SL.ntiles = (int)tiles.size();
   SL.tiles_dev = shard_upload(sh, tiles);
+  if (k >= kPhaseMinLevel) {
+    LevelLayout lay;
+    for (size_t p = 0; p < prog.panels.size(); ++p) {
+      lay.width.push_back(SL.width[p]);
+      lay.rowbase.push_back(SL.rowbase.data() + SL.slot_off[p]);
+      lay.dest.push_back(SL.dest.data() + SL.slot_off[p]);
+      lay.panel_off.push_back(SL.panel_off[p]);
+    }
+    lay.in_stride = L.in_stride;
+    lay.out_stride = L.out_stride;
+    lay.block_stride = s_in;
+    auto up = [&](const auto& v) { return shard_upload(sh, v); };
+    build_phase_devs(prog, lay, L.coef, up, SL.phases);
+    build_p1_dev(prog, lay, up, SL.p1);
+  }
 }
 
 }  // namespace
@@ -935,6 +1003,31 @@ int snfft_shard_level(const snfft_shard* sh, int k, const double* in_dev, double
     g_force_table_driven = true;  // the generated level-8 programs assume the full column pitch
     cudaError_t e = launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, in_dev, out_dev, groups,
                                  inverse != 0, sh->plan->num_sms, (cudaStream_t)stream);
+    g_force_table_driven = saved;
+    CUDA_OK(e);
+  });
+}
+
+int snfft_shard_level_scratch(const snfft_shard* sh, int k, double* x_dev, double* s_dev, int64_t groups,
+                              int inverse, void* stream) {
+  return guarded([&] {
+    if (!sh) throw InvalidArg("shard is null");
+    require_device(sh->plan);
+    if (k <= sh->m || k > sh->plan->host.n) throw InvalidArg("level k must be in m+1..n");
+    if (!x_dev || !s_dev || x_dev == s_dev) throw InvalidArg("bad buffers");
+    if (groups < 0) throw InvalidArg("groups < 0");
+    DeviceGuard guard(sh->plan->device);
+    const ShardLevel& SL = sh->levels[k];
+    if (!SL.phases.empty() && !g_force_table_driven) {
+      run_phases(SL.phases, SL.p1, sh->plan->num_sms, x_dev, s_dev, groups, inverse != 0, (cudaStream_t)stream);
+      return;
+    }
+    const bool saved = g_force_table_driven;
+    g_force_table_driven = true;
+    cudaError_t e = inverse ? launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, s_dev, x_dev, groups, true,
+                                           sh->plan->num_sms, (cudaStream_t)stream)
+                            : launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, x_dev, s_dev, groups, false,
+                                           sh->plan->num_sms, (cudaStream_t)stream);
     g_force_table_driven = saved;
     CUDA_OK(e);
   });

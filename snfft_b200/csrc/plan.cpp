@@ -390,6 +390,7 @@ void build_phases(PanelProgram& P) {
         local[s] = (int)q;
         const bool fin = last_writer[s] >= b0 && last_writer[s] < b1;
         ph.rows.push_back(PhaseRow{P.rowbase[s], P.dest[s], fin ? 1u : 0u});
+        ph.row_slot.push_back((uint32_t)s);
       }
       for (int b : gblocks[g]) {
         const Block& blk = P.blocks[b];

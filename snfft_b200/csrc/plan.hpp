@@ -75,6 +75,7 @@ struct PanelPhase {
   int stage_lo = 0, stage_hi = 0;  // stages [lo, hi], 1-based
   std::vector<PhaseGroup> groups;  // row_off / blk_off relative to this panel's vectors
   std::vector<PhaseRow> rows;
+  std::vector<uint32_t> row_slot;  // slot of every entry of `rows` (host only; shards remap offsets)
   std::vector<PhaseBlock> blocks;
   int max_rows = 0;
 };

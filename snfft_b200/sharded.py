@@ -126,9 +126,11 @@ class ShardedPlan:
         groups = math.factorial(self.n) // math.factorial(k)
         size_out = self.sizes[self.rank][k - 1] * k if inverse else self.sizes[self.rank][k]
         out = torch.empty(groups * size_out, dtype=torch.float64, device=x.device)
+        # x is always an intermediate of this class, so the forward direction may overwrite it
+        xs, ss = (out, x) if inverse else (x, out)
         with torch.cuda.device(self.device):
-            N.check(N.lib.snfft_shard_level(self._h, k, N.ptr(x), N.ptr(out), groups, int(inverse),
-                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            N.check(N.lib.snfft_shard_level_scratch(self._h, k, N.ptr(xs), N.ptr(ss), groups, int(inverse),
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out
 
     def _index(self, r, like):
