@@ -142,8 +142,15 @@ class ShardedPlan:
 
     # ------------------------------------------------------------------ the one exchange
     def _exchange(self, send, recv):
-        """send[q] -> rank q, recv[q] <- rank q (point-to-point, works on NCCL and Gloo)."""
+        """send[q] -> rank q, recv[q] <- rank q.  NCCL: one all-to-all (uneven splits); Gloo has no
+        all-to-all for this, so there it is batched point-to-point."""
         import torch.distributed as dist
+        if self.world == 1:
+            recv[0].copy_(send[0])
+            return
+        if dist.get_backend(self.group) == 'nccl':
+            dist.all_to_all(recv, send, group=self.group)
+            return
         recv[self.rank].copy_(send[self.rank])
         ops = []
         for q in range(self.world):
@@ -151,9 +158,8 @@ class ShardedPlan:
                 continue
             ops.append(dist.P2POp(dist.isend, send[q], self._peer(q), group=self.group))
             ops.append(dist.P2POp(dist.irecv, recv[q], self._peer(q), group=self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
 
     def _peer(self, q):
         import torch.distributed as dist
