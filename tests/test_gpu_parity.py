@@ -279,3 +279,43 @@ def test_host_pipeline_matches_device_path():
     want = plan.forward(f.cuda(), 'lex').cpu()
     assert torch.equal(spec, want)
     assert ((back - f).norm() / f.norm()).item() < TOL
+
+
+@pytest.mark.parametrize('n', [11, 12])
+def test_s11_s12_properties(n):
+    """BASELINE configs[4]: S_12 (479 M elements, 3.8 GB per buffer) on one GPU; the reference and
+    the oracle cannot run here, so: round trip, Plancherel, and a sparse-support input checked per
+    irrep against rho_lambda(sigma) from the device YOR kernel (irreps up to dimension 320)."""
+    plan = get_plan(n)
+    nf = math.factorial(n)
+    gen = torch.Generator(device='cuda').manual_seed(n)
+    x = torch.randn(nf, dtype=torch.float64, device='cuda', generator=gen)
+    spec = plan.forward(x, 'coset')
+    back = plan.inverse(spec, 'coset')
+    assert ((back - x).norm() / x.norm()).item() < TOL
+    del back
+    parts, dims, offs = plan.layout()
+    lhs = sum(d * spec[o:o + d * d].pow(2).sum().item() for d, o in zip(dims, offs))
+    rhs = nf * x.pow(2).sum().item()
+    assert abs(lhs - rhs) / rhs < 1e-12
+    del x, spec
+    torch.cuda.empty_cache()
+    rng = np.random.default_rng(n)
+    sig = [tuple(int(v) + 1 for v in rng.permutation(n)) for _ in range(2)]
+    coef = rng.standard_normal(2)
+    sparse = torch.zeros(nf, dtype=torch.float64, device='cuda')
+    for s, c in zip(sig, coef):
+        sparse[O.lex_rank(s)] += c
+    sp = plan.forward(sparse, 'lex')
+    del sparse
+    perms = torch.tensor(sig, dtype=torch.int32, device='cuda')
+    cdev = torch.from_numpy(coef).cuda()
+    checked = 0
+    for i, (p, d, o) in enumerate(zip(parts, dims, offs)):
+        if d > 320:
+            continue
+        want = (cdev[:, None, None] * plan.yor(i, perms)).sum(dim=0)
+        got = sp[o:o + d * d].reshape(d, d)
+        assert ((got - want).norm() / want.norm()).item() < TOL, p
+        checked += 1
+    assert checked >= 10
