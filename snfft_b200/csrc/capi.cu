@@ -210,13 +210,16 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
     std::vector<PhaseBlock> blocks;
     int64_t items = 0;
     int max_rows = 1;
+    for (const PanelProgram& P : prog.panels) max_rows = std::max(max_rows, P.phases[ph].max_rows);
+    // more columns per lane amortise the per-block table loads; keep a warp's tile <= 12 KB
+    const int cpl = max_rows <= 12 ? 4 : (max_rows <= 24 ? 2 : 1);
     for (size_t p = 0; p < prog.panels.size(); ++p) {
       const PanelProgram& P = prog.panels[p];
       const PanelPhase& pp = P.phases[ph];
       const int w = lay.width[p];
       PhasePanelDev pd;
       pd.d = w;
-      pd.tiles = (w + 31) / 32;
+      pd.tiles = (w + 32 * cpl - 1) / (32 * cpl);
       pd.grp_off = (int32_t)groups.size();
       pd.ngroups = w > 0 ? (int32_t)pp.groups.size() : 0;
       pd.item_off = items;
@@ -246,6 +249,7 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
     D.out_stride = lay.out_stride;
     D.npanels = (int32_t)panels.size();
     D.max_rows = max_rows;
+    D.cols_per_lane = cpl;
     out_devs.push_back(D);
   }
 }

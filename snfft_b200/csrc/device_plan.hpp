@@ -45,7 +45,7 @@ struct Tile {
 // Row-group phase of a level (levels >= 9): see plan.hpp
 struct PhasePanelDev {
   int32_t d;         // columns of the panel
-  int32_t tiles;     // ceil(d / 32)
+  int32_t tiles;     // ceil(d / (32 * cols_per_lane))
   int32_t grp_off;   // first group in PhaseDev::groups
   int32_t ngroups;
   int64_t item_off;  // prefix sum of ngroups * tiles
@@ -61,6 +61,7 @@ struct PhaseDev {
   int64_t in_stride, out_stride;  // group strides of the X-side and spectrum-side buffers
   int32_t npanels;
   int32_t max_rows;
+  int32_t cols_per_lane;  // 1, 2 or 4: a warp covers 32 * cols_per_lane columns (PhasePanelDev::tiles)
 };
 
 // In-place phase 1 of a large level as generated register programs: one entry per (panel, upper

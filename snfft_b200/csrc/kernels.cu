@@ -525,12 +525,37 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int kPhaseWarps = 8;
 
-template <bool INV>
+// y[c][a] = sum_b cm[a][b] x[c][b] for CPL columns with one load of the coefficients
+template <int M, int CPL>
+__device__ __forceinline__ void block_apply(const double* __restrict__ cmat, const uint8_t* loc, double* col) {
+  double cm[M * M];
+#pragma unroll
+  for (int i = 0; i < M * M; ++i) cm[i] = __ldg(cmat + i);
+#pragma unroll
+  for (int cc = 0; cc < CPL; ++cc) {
+    double x[M], y[M];
+#pragma unroll
+    for (int b = 0; b < M; ++b) x[b] = col[loc[b] * (32 * CPL) + cc * 32];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double acc = cm[a * M] * x[0];
+#pragma unroll
+      for (int b = 1; b < M; ++b) acc = fma(cm[a * M + b], x[b], acc);
+      y[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) col[loc[a] * (32 * CPL) + cc * 32] = y[a];
+  }
+}
+
+// CPL = columns per lane: a warp covers 32 * CPL columns of one row group (tile = [rows][32 * CPL])
+template <bool INV, int CPL>
 __global__ void __launch_bounds__(kPhaseWarps * 32)
 phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside, int64_t lgroups) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* col = sm + (size_t)warp * P.max_rows * 32 + lane;
+  constexpr int W = 32 * CPL;
+  double* col = sm + (size_t)warp * P.max_rows * W + lane;
   for (int64_t item = (int64_t)blockIdx.x * kPhaseWarps + warp; item < P.nitems;
        item += (int64_t)gridDim.x * kPhaseWarps) {
     int pi = 0;
@@ -538,37 +563,38 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
     const PhasePanelDev pan = P.panels[pi];
     const int64_t rem = item - pan.item_off;
     const int group = (int)(rem / pan.tiles), tile = (int)(rem - (int64_t)group * pan.tiles);
-    const int c = tile * 32 + lane;
-    const bool active = c < pan.d;
+    const int c0 = tile * W + lane;
     const PhaseGroup G = P.groups[pan.grp_off + group];
     const PhaseRow* __restrict__ rows = P.rows + G.row_off;
     const PhaseBlock* __restrict__ blocks = P.blocks + G.blk_off;
     for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
-      double* xs = xside + lg * P.in_stride + c;
-      double* ss = sside + lg * P.out_stride + c;
-      if (active) {
-        for (int r = 0; r < G.nrows; ++r) {
-          const PhaseRow row = rows[r];
-          col[r * 32] = (INV && row.final) ? ss[row.dest] : xs[row.xoff];
-        }
-        for (int bi = 0; bi < G.nblk; ++bi) {
-          const PhaseBlock b = blocks[INV ? G.nblk - 1 - bi : bi];
-          double x[kMaxBlock], y[kMaxBlock];
+      double* xs = xside + lg * P.in_stride + c0;
+      double* ss = sside + lg * P.out_stride + c0;
+#pragma unroll 2
+      for (int r = 0; r < G.nrows; ++r) {
+        const PhaseRow row = rows[r];
+        const double* src = (INV && row.final) ? ss + row.dest : xs + row.xoff;
 #pragma unroll
-          for (int i = 0; i < kMaxBlock; ++i)
-            if (i < b.m) x[i] = col[b.loc[i] * 32];
-          matvec_m(b.m, P.coef + (INV ? b.coef_i : b.coef_f), x, y);
+        for (int cc = 0; cc < CPL; ++cc)
+          if (c0 + cc * 32 < pan.d) col[r * W + cc * 32] = src[cc * 32];
+      }
+      for (int bi = 0; bi < G.nblk; ++bi) {
+        const PhaseBlock b = blocks[INV ? G.nblk - 1 - bi : bi];
+        const double* cmat = P.coef + (INV ? b.coef_i : b.coef_f);
+        switch (b.m) {
+          case 2: block_apply<2, CPL>(cmat, b.loc, col); break;
+          case 3: block_apply<3, CPL>(cmat, b.loc, col); break;
+          case 4: block_apply<4, CPL>(cmat, b.loc, col); break;
+          default: block_apply<5, CPL>(cmat, b.loc, col); break;
+        }
+      }
+#pragma unroll 2
+      for (int r = 0; r < G.nrows; ++r) {
+        const PhaseRow row = rows[r];
+        double* dst = (!INV && row.final) ? ss + row.dest : xs + row.xoff;
 #pragma unroll
-          for (int i = 0; i < kMaxBlock; ++i)
-            if (i < b.m) col[b.loc[i] * 32] = y[i];
-        }
-        for (int r = 0; r < G.nrows; ++r) {
-          const PhaseRow row = rows[r];
-          if (!INV && row.final)
-            ss[row.dest] = col[r * 32];
-          else
-            xs[row.xoff] = col[r * 32];
-        }
+        for (int cc = 0; cc < CPL; ++cc)
+          if (c0 + cc * 32 < pan.d) dst[cc * 32] = col[r * W + cc * 32];
       }
     }
   }
@@ -814,8 +840,12 @@ cudaError_t prepare_kernels() {
   cudaError_t e;
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<false>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false, 1>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true, 1>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false, 2>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true, 2>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false, 4>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true, 4>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
@@ -895,10 +925,10 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
-                         int num_sms, cudaStream_t stream) {
-  if (lgroups <= 0 || P.nitems <= 0) return cudaSuccess;
-  const size_t smem = (size_t)kPhaseWarps * P.max_rows * 32 * sizeof(double);
+template <int CPL>
+static cudaError_t launch_phase_cpl(const PhaseDev& P, double* xside, double* sside, int64_t lgroups,
+                                    bool inverse, int num_sms, cudaStream_t stream) {
+  const size_t smem = (size_t)kPhaseWarps * P.max_rows * 32 * CPL * sizeof(double);
   int64_t gy = lgroups < 64 ? lgroups : 64;
   int64_t gx = (P.nitems + kPhaseWarps - 1) / kPhaseWarps;
   const int64_t want = 16LL * num_sms;  // enough CTAs to fill the machine; the rest is grid-stride
@@ -907,10 +937,20 @@ cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_
   dim3 grid((unsigned)gx, (unsigned)gy);
   LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
   if (inverse)
-    phase_kernel<true><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+    phase_kernel<true, CPL><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
   else
-    phase_kernel<false><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+    phase_kernel<false, CPL><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
   return cudaGetLastError();
+}
+
+cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
+                         int num_sms, cudaStream_t stream) {
+  if (lgroups <= 0 || P.nitems <= 0) return cudaSuccess;
+  switch (P.cols_per_lane) {
+    case 4: return launch_phase_cpl<4>(P, xside, sside, lgroups, inverse, num_sms, stream);
+    case 2: return launch_phase_cpl<2>(P, xside, sside, lgroups, inverse, num_sms, stream);
+    default: return launch_phase_cpl<1>(P, xside, sside, lgroups, inverse, num_sms, stream);
+  }
 }
 
 cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
