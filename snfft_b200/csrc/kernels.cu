@@ -94,6 +94,9 @@ constexpr int kThreads = 256;
 #ifndef SNFFT_FUSED_THREADS
 #define SNFFT_FUSED_THREADS 256
 #endif
+#ifndef SNFFT_L8_SUPER
+#define SNFFT_L8_SUPER 30
+#endif
 #ifndef SNFFT_L8_MINBLOCKS
 #define SNFFT_L8_MINBLOCKS 2
 #endif
@@ -317,6 +320,16 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
     double* gout = out + g0 * S::kFact;
     const int n4 = ng * S::kS4Blocks;  // S_4 blocks in this chunk (<= 210)
     const int nelem = n4 * 24;
+#ifndef SNFFT_NO_L2_PREFETCH
+    if (K0 == 7 && tid == 0) {
+      // the next group of this CTA is pulled into L2 while this one is transformed
+      const int64_t gn = g0 + (int64_t)gridDim.x * S::kGroups;
+      if (gn < groups)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + gn * S::kFact),
+                     "r"(5040 * 8)
+                     : "memory");
+    }
+#endif
     if (!INV) {
       // ---- coalesced stage-in: S_4 blocks padded to stride kS4 ---------------------------------
       if (K0 == 7) {
@@ -388,8 +401,18 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
       }
     } else {
       if (K0 == 7) {
-        for (int e = tid; e < 5040 / 2; e += nthreads)
-          reinterpret_cast<double2*>(Q + kFusedC)[e] = reinterpret_cast<const double2*>(gin)[e];
+        constexpr int kPer = (2520 + kFusedThreads - 1) / kFusedThreads;
+        double2 v[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          const int e = tid + j * kFusedThreads;
+          if (e < 2520) v[j] = __ldg(reinterpret_cast<const double2*>(gin) + e);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          const int e = tid + j * kFusedThreads;
+          if (e < 2520) reinterpret_cast<double2*>(Q + kFusedC)[e] = v[j];
+        }
         __syncthreads();
         fused_level7_phase2<true>(P, Q, Q + kFusedC);
         __syncthreads();
@@ -450,8 +473,12 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
 // them together with X_6..X_8 from global memory and stores the finished rows.  The inverse runs
 // phase 2 transposed first.
 // ---------------------------------------------------------------------------------------------
+// CTAs are numbered super-chunk-major (kL8Super consecutive groups, all panels, heaviest panel
+// first): the d_mu-double row segments that neighbouring panels write into (read from) the same
+// 32-byte sectors then meet in L2 instead of costing a DRAM fill each.
+constexpr int kL8Super = SNFFT_L8_SUPER;
 struct L8Launch {
-  int first_cta[gen::kL8NumPanels + 1];  // CTAs [first_cta[p], first_cta[p+1]) work on panel order[p]
+  int first_cta[gen::kL8NumPanels + 1];  // within a super-chunk: CTAs [first_cta[p], first_cta[p+1]) -> order[p]
   int order[gen::kL8NumPanels];          // panels, heaviest first
   int cap[gen::kL8NumPanels];            // groups per CTA, indexed like `order`
 };
@@ -460,12 +487,16 @@ template <bool INV>
 __global__ void __launch_bounds__(kL8Threads, SNFFT_L8_MINBLOCKS)
 level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict__ out, int64_t groups) {
   extern __shared__ double cbuf[];
+  const int per_super = launch.first_cta[gen::kL8NumPanels];
+  const int super = blockIdx.x / per_super, within = blockIdx.x - super * per_super;
   int slot = 0;
-  while (slot + 1 < gen::kL8NumPanels && (int)blockIdx.x >= launch.first_cta[slot + 1]) ++slot;
+  while (slot + 1 < gen::kL8NumPanels && within >= launch.first_cta[slot + 1]) ++slot;
   const int panel = launch.order[slot], cap = launch.cap[slot];
   const int d = gen::kL8PanelDim[panel], in_off = gen::kL8PanelInOff[panel];
-  const int64_t g0 = (int64_t)((int)blockIdx.x - launch.first_cta[slot]) * cap;
-  const int ng = (int)min((int64_t)cap, groups - g0);
+  const int64_t g0 = (int64_t)super * kL8Super + (int64_t)(within - launch.first_cta[slot]) * cap;
+  const int64_t gend = min(groups, (int64_t)(super + 1) * kL8Super);
+  if (g0 >= gend) return;
+  const int ng = (int)min((int64_t)cap, gend - g0);
   const int cgroup = 5 * d * d;  // C_5 rows of one group
   // forward: in = 8 packed S_7 spectra per group, out = packed S_8 spectrum; inverse: swapped
   const double* xin = in + g0 * 40320;
@@ -507,6 +538,16 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
         });
   };
   if (!INV) {
+#ifndef SNFFT_NO_L8_PREFETCH
+    // X_6..X_8 (three runs of d*d doubles per group) are only read in phase 2: pull them into L2 now
+    if ((int)threadIdx.x < 3 * ng) {
+      const int gb = threadIdx.x / 3, i = 5 + (int)threadIdx.x - 3 * gb;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(xin + (int64_t)gb * 40320 + i * 5040 + in_off);
+      const uintptr_t a0 = a & ~(uintptr_t)15;
+      const unsigned bytes = (unsigned)(((a + (uintptr_t)d * d * 8 + 15) & ~(uintptr_t)15) - a0);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+    }
+#endif
     phase1();
     __syncthreads();
     phase2();
@@ -872,13 +913,15 @@ cudaError_t launch_level8(const double* in, double* out, int64_t groups, bool in
     const int d = dims[order[i]];
     int cap = kL8SmemDoubles / (5 * d * d);
     if (cap > 64) cap = 64;
+    if (cap > kL8Super) cap = kL8Super;
     if (cap < 1) cap = 1;
     launch.order[i] = order[i];
     launch.cap[i] = cap;
     launch.first_cta[i] = (int)total;
-    total += (groups + cap - 1) / cap;
+    total += (kL8Super + cap - 1) / cap;
   }
-  launch.first_cta[gen::kL8NumPanels] = (int)total;
+  launch.first_cta[gen::kL8NumPanels] = (int)total;  // CTAs per super-chunk
+  total *= (groups + kL8Super - 1) / kL8Super;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
   LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
   const size_t smem = kL8SmemDoubles * sizeof(double);
