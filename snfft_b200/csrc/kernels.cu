@@ -734,6 +734,137 @@ __global__ void reorder_kernel(int n, Facts F, const uint32_t* __restrict__ tabl
   }
 }
 
+// Tiled reorder for n >= kTileMinN.  With R = 5 top coset digits and S = 4 low ones the index map
+// factors: the top digits fix the last R letters of sigma (an arrangement A of a value set V) and
+// leave the first n-R letters in increasing order, so for fixed V and fixed middle digits
+//   coset[top(A) + mid * S! + low] = lex[base(V, mid, low) + A],   A < R!, low < S!
+// i.e. every tile is a (S! x R!) transpose between 960-byte lexicographic runs and 192-byte
+// coset-major runs, both sector aligned (the element-wise gather above moves 16x the bytes).
+constexpr int kTileR = 5, kTileS = 4, kTileRF = 120, kTileSF = 24, kTileMinN = 9;
+constexpr int kTilePitch = kTileSF + 1;
+constexpr int kTileThreads = 256;
+
+template <bool TO_COSET>
+__global__ void __launch_bounds__(kTileThreads)
+reorder_tiled_kernel(int n, Facts F, int nsubsets, int64_t nmid, int mids_per_cta,
+                     const double* __restrict__ src, double* __restrict__ dst, int64_t batch) {
+  __shared__ double tile[kTileRF * kTilePitch];
+  __shared__ int64_t top_off[kTileRF];
+  __shared__ int64_t lex_base[kTileSF];
+  __shared__ int iota[kMaxN + 1];  // iota[x] = x-th smallest value outside V (1-based)
+  const int tid = threadIdx.x;
+  const int m = n - kTileR;  // letters permuted by the middle and low digits
+  const int64_t chunks = (nmid + mids_per_cta - 1) / mids_per_cta;
+  const int64_t total = F.f[n];
+  for (int64_t work = blockIdx.x; work < (int64_t)nsubsets * chunks; work += gridDim.x) {
+    const int vi = (int)(work / chunks);
+    const int64_t mid0 = (work - (int64_t)vi * chunks) * mids_per_cta;
+    __syncthreads();
+    if (tid < kTileRF) {
+      // unrank the subset (lexicographic combinadic), every thread for itself: R values
+      int V[kTileR];
+      {
+        int rem = vi, x = 1;
+        for (int j = 0; j < kTileR; ++j) {
+          for (;; ++x) {
+            // subsets that continue with x at position j: C(n - x, R - 1 - j)
+            int c = 1;
+            const int top = n - x, k = kTileR - 1 - j;
+            for (int t = 1; t <= k; ++t) c = c * (top - k + t) / t;
+            if (top < k) c = 0;
+            if (rem < c) break;
+            rem -= c;
+          }
+          V[j] = x++;
+        }
+      }
+      if (tid == 0) {
+        int j = 0, cnt = 0;
+        for (int x = 1; x <= n; ++x) {
+          if (j < kTileR && V[j] == x) { ++j; continue; }
+          iota[++cnt] = x;
+        }
+      }
+      // arrangement tid of V: suffix letters sigma(m+1..n) by Lehmer decoding of tid
+      int suf[kTileR], pool[kTileR];
+#pragma unroll
+      for (int j = 0; j < kTileR; ++j) pool[j] = V[j];
+      int a = tid;
+      int fact = kTileRF;
+#pragma unroll
+      for (int j = 0; j < kTileR; ++j) {
+        fact /= (kTileR - j);
+        const int q = a / fact;
+        a -= q * fact;
+        suf[j] = pool[q];
+        for (int t = q; t + 1 < kTileR - j; ++t) pool[t] = pool[t + 1];
+      }
+      // top digits: at level k the letter suf[k-m-1] sits at position value - #(extracted smaller)
+      int64_t off = 0;
+#pragma unroll
+      for (int k = kTileR - 1; k >= 0; --k) {
+        int pos = suf[k];
+#pragma unroll
+        for (int t = k + 1; t < kTileR; ++t) pos -= suf[t] < suf[k];
+        off += (int64_t)(pos - 1) * F.f[m + k];
+      }
+      top_off[tid] = off;
+    }
+    for (int mi = 0; mi < mids_per_cta && mid0 + mi < nmid; ++mi) {
+      const int64_t mid = mid0 + mi;
+      __syncthreads();
+      if (tid >= 128 && tid < 128 + kTileSF) {
+        const int low = tid - 128;
+        int q[kMaxN + 1];
+#pragma unroll
+        for (int x = 1; x <= kMaxN; ++x) q[x] = x;
+        const int64_t flat = mid * kTileSF + low;
+        for (int k = m; k >= 2; --k) {
+          const int i = (int)((flat / F.f[k - 1]) % k) + 1;
+          const int first = q[i];
+          for (int x = i; x < k; ++x) q[x] = q[x + 1];
+          q[k] = first;
+        }
+        int64_t base = 0;
+        for (int a = 1; a <= m; ++a) {
+          int smaller = iota[q[a]] - q[a];
+          for (int b = a + 1; b <= m; ++b) smaller += q[b] < q[a];
+          base += smaller * F.f[n - a];
+        }
+        lex_base[low] = base;
+      }
+      __syncthreads();
+      const int64_t coset0 = mid * kTileSF;
+      for (int64_t b = blockIdx.y; b < batch; b += gridDim.y) {
+        const double* __restrict__ sb = src + b * total;
+        double* __restrict__ db = dst + b * total;
+        if (TO_COSET) {
+          for (int e = tid; e < kTileRF * kTileSF; e += kTileThreads) {
+            const int low = e / kTileRF, a = e - low * kTileRF;
+            tile[a * kTilePitch + low] = sb[lex_base[low] + a];
+          }
+          __syncthreads();
+          for (int e = tid; e < kTileRF * kTileSF; e += kTileThreads) {
+            const int a = e / kTileSF, low = e - a * kTileSF;
+            db[top_off[a] + coset0 + low] = tile[a * kTilePitch + low];
+          }
+        } else {
+          for (int e = tid; e < kTileRF * kTileSF; e += kTileThreads) {
+            const int a = e / kTileSF, low = e - a * kTileSF;
+            tile[a * kTilePitch + low] = sb[top_off[a] + coset0 + low];
+          }
+          __syncthreads();
+          for (int e = tid; e < kTileRF * kTileSF; e += kTileThreads) {
+            const int low = e / kTileRF, a = e - low * kTileRF;
+            db[lex_base[low] + a] = tile[a * kTilePitch + low];
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // rho_lambda(sigma): apply the generator word to the identity, one CTA per permutation
 // ---------------------------------------------------------------------------------------------
@@ -1056,11 +1187,28 @@ cudaError_t launch_reorder(int n, const uint32_t* table, const double* src, doub
   if (batch <= 0) return cudaSuccess;
   const Facts F = make_facts();
   const int64_t total = F.f[n];
+  LaunchScope scope(kKindReorder, stream);
+  if (n >= kTileMinN && !g_force_table_driven) {
+    int nsubsets = 1;  // C(n, R)
+    for (int t = 1; t <= kTileR; ++t) nsubsets = nsubsets * (n - kTileR + t) / t;
+    const int64_t nmid = F.f[n - kTileR] / kTileSF;
+    int64_t by = batch < 16 ? batch : 16;
+    // enough CTAs for ~16 waves of the machine, at most 8 tiles of one subset per CTA
+    int mids = 1;
+    while (mids < 8 && (int64_t)nsubsets * ((nmid + mids) / (mids + 1)) * by >= 148 * 8 * 16) ++mids;
+    int64_t bx = (int64_t)nsubsets * ((nmid + mids - 1) / mids);
+    if (bx > 0x7fffffffLL) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)bx, (unsigned)by);
+    if (to_coset)
+      reorder_tiled_kernel<true><<<grid, kTileThreads, 0, stream>>>(n, F, nsubsets, nmid, mids, src, dst, batch);
+    else
+      reorder_tiled_kernel<false><<<grid, kTileThreads, 0, stream>>>(n, F, nsubsets, nmid, mids, src, dst, batch);
+    return cudaGetLastError();
+  }
   int64_t bx = (total + 255) / 256;
   if (bx > 2048) bx = 2048;
   int64_t by = batch < 64 ? batch : 64;
   dim3 grid((unsigned)bx, (unsigned)by);
-  LaunchScope scope(kKindReorder, stream);
   if (to_coset)
     reorder_kernel<true><<<grid, 256, 0, stream>>>(n, F, table, src, dst, batch);
   else

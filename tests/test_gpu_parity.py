@@ -171,6 +171,40 @@ def test_reorder_kernels():
         assert np.array_equal(plan.reorder(dev(to_coset), False).cpu().numpy(), x)
 
 
+@pytest.mark.parametrize('n', [9, 10, 11])
+def test_reorder_tiled_kernel(n):
+    # n >= 9 uses the tiled transpose kernel; the host index table is the checker
+    plan = get_plan(n)
+    c2l = plan.coset_to_lex()
+    size = math.factorial(n)
+    batch = 3 if n < 11 else 1
+    x = torch.arange(batch * size, dtype=torch.float64, device='cuda').reshape(batch, size)
+    to_coset = plan.reorder(x, True)
+    want = torch.from_numpy(c2l.astype(np.float64)).cuda()
+    for b in range(batch):
+        assert torch.equal(to_coset[b], want + float(b * size))
+    assert torch.equal(plan.reorder(to_coset, False), x)
+    del x, to_coset, want
+    torch.cuda.empty_cache()
+
+
+def test_reorder_tiled_matches_elementwise_s12():
+    from snfft_b200 import _native as N
+    plan = get_plan(12)
+    x = torch.arange(plan.size, dtype=torch.float64, device='cuda').reshape(1, -1)
+    tiled = plan.reorder(x, True)
+    N.lib.snfft_debug_force_table_driven(1)
+    try:
+        plain = plan.reorder(x, True)
+    finally:
+        N.lib.snfft_debug_force_table_driven(0)
+    assert torch.equal(tiled, plain)
+    del plain
+    assert torch.equal(plan.reorder(tiled, False), x)
+    del x, tiled
+    torch.cuda.empty_cache()
+
+
 def test_yor_device_matches_reference_golden(golden_small):
     names = [k for k in golden_small.files if k.startswith('yor_')]
     for name in names:
