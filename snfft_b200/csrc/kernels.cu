@@ -278,14 +278,85 @@ __device__ __forceinline__ void for_each_chunk(int seg_begin, int seg_end, Count
   }
 }
 
+// Static variant for a full S_7 group (K0 == 7): the (segment, 32-instance chunk) list of a phase
+// is a compile-time table ordered heaviest segment first, so a warp reads its tasks instead of
+// scanning the segment list, and the second round of a phase holds the lightest chunks.
+template <int MAXT>
+struct ChunkTable {
+  int n;
+  unsigned char seg[MAXT];
+  unsigned short inst0[MAXT];
+  unsigned short count[MAXT];
+};
+template <int MAXT, class Count, class Cost>
+constexpr ChunkTable<MAXT> make_chunk_table(int nseg, Count count, Cost cost) {
+  ChunkTable<MAXT> T{};
+  int weight[MAXT] = {};
+  for (int sgm = 0; sgm < nseg; ++sgm)
+    for (int i = 0; i < count(sgm); i += 32) {
+      int at = T.n++;
+      // insertion keeps the list sorted by cost, heaviest first (stable)
+      while (at > 0 && weight[at - 1] < cost(sgm)) {
+        T.seg[at] = T.seg[at - 1];
+        T.inst0[at] = T.inst0[at - 1];
+        T.count[at] = T.count[at - 1];
+        weight[at] = weight[at - 1];
+        --at;
+      }
+      T.seg[at] = (unsigned char)sgm;
+      T.inst0[at] = (unsigned short)i;
+      T.count[at] = (unsigned short)count(sgm);
+      weight[at] = cost(sgm);
+    }
+  return T;
+}
+struct L5Count { constexpr int operator()(int p) const { return 42 * gen::kL5Dims[p]; } };
+struct L5Cost { constexpr int operator()(int p) const { return gen::kL5Dims[p]; } };
+struct L6Count { constexpr int operator()(int p) const { return 7 * gen::kL6Dims[p]; } };
+struct L6Cost { constexpr int operator()(int p) const { return gen::kL6Dims[p]; } };
+struct P1Count { constexpr int operator()(int s) const { return gen::kL7P1SigmaStart[s + 1] - gen::kL7P1SigmaStart[s]; } };
+struct P1Cost { constexpr int operator()(int) const { return 1; } };
+struct P2Count { constexpr int operator()(int p) const { return gen::kL7P2MaxInst[p]; } };
+struct P2Cost { constexpr int operator()(int p) const { return gen::kL7PanelDim[p]; } };
+__device__ constexpr ChunkTable<24> kTabL5 = make_chunk_table<24>(gen::kL5Panels, L5Count{}, L5Cost{});
+__device__ constexpr ChunkTable<16> kTabL6 = make_chunk_table<16>(gen::kL6Panels, L6Count{}, L6Cost{});
+__device__ constexpr ChunkTable<16> kTabP1 = make_chunk_table<16>(7, P1Count{}, P1Cost{});
+__device__ constexpr ChunkTable<16> kTabP2 = make_chunk_table<16>(gen::kL7NumPanels, P2Count{}, P2Cost{});
+
+template <int MAXT, class Body>
+__device__ __forceinline__ void for_each_static_chunk(const ChunkTable<MAXT>& T, Body body) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int t = warp; t < T.n; t += kFusedThreads / 32) {
+    const int inst = T.inst0[t] + lane;
+    if (inst < T.count[t]) body((int)T.seg[t], inst);
+  }
+}
+
+template <int LEVEL, bool INV, class AddrIn, class AddrOut>
+__device__ __forceinline__ void run_generated_static(AddrIn in_of, AddrOut out_of) {
+  constexpr int nsub = LEVEL == 5 ? 42 : 7;
+  auto body = [&](int p, int inst) {
+    const int c = inst / nsub;
+    const int g = inst - c * nsub;
+    if (LEVEL == 5)
+      gen::l5_run<INV>(p, in_of(g) + c, out_of(g) + c);
+    else
+      gen::l6_run<INV>(p, in_of(g) + c, out_of(g) + c);
+  };
+  if (LEVEL == 5)
+    for_each_static_chunk(kTabL5, body);
+  else
+    for_each_static_chunk(kTabL6, body);
+}
+
 // level 7 inside the fused kernel (one S_7 group): phase 1 turns the rows X_1..X_5 of every upper
 // chain (bufA, padded S_6 blocks) into C_5 rows (bufB, kind layout, panel region at 5*in_off);
 // phase 2 combines them with X_6, X_7 and stores the finished rows to global memory.
 template <bool INV>
 __device__ __forceinline__ void fused_level7_phase1(double* bufA, double* bufB) {
-  for_each_chunk(
-      0, 7, [](int sigma) { return gen::kL7P1SigmaStart[sigma + 1] - gen::kL7P1SigmaStart[sigma]; },
-      [&](int sigma, int inst) {
+  for_each_static_chunk(
+      kTabP1, [&](int sigma, int inst) {
         const int at = gen::kL7P1SigmaStart[sigma] + inst;
         const int e = gen::kL7P1InstEntry[at], c = gen::kL7P1InstCol[at];
         const int dmu = gen::kL7P1DMu[e], in_off = gen::kL7P1InOff[e], ubase = gen::kL7P1Base[e];
@@ -300,9 +371,8 @@ __device__ __forceinline__ void fused_level7_phase1(double* bufA, double* bufB) 
 
 template <bool INV>
 __device__ __forceinline__ void fused_level7_phase2(double* bufA, double* bufB, double* gspec) {
-  for_each_chunk(
-      0, gen::kL7NumPanels, [](int panel) { return gen::kL7P2MaxInst[panel]; },
-      [&](int panel, int inst) { gen::l7p2_panel<INV>(panel, inst, bufB, bufA, gspec); });
+  for_each_static_chunk(
+      kTabP2, [&](int panel, int inst) { gen::l7p2_panel<INV>(panel, inst, bufB, bufA, gspec); });
 }
 
 template <int K0, bool INV>
@@ -376,6 +446,9 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
         if (K0 == 5)
           run_generated_level<5, false>(nsub, [&](int g) { return (const double*)P + g * gen::kG5; },
                                         [&](int g) { return gout + (int64_t)g * 120; });
+        else if (K0 == 7)
+          run_generated_static<5, false>([&](int g) { return (const double*)P + g * gen::kG5; },
+                                         [&](int g) { return Q + g * gen::kS5 + (g / 6) * gen::kP6; });
         else
           run_generated_level<5, false>(nsub, [&](int g) { return (const double*)P + g * gen::kG5; },
                                         [&](int g) { return Q + g * gen::kS5 + (g / 6) * gen::kP6; });
@@ -387,8 +460,8 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
           run_generated_level<6, false>(nsub, [&](int g) { return (const double*)Q + g * gen::kG6; },
                                         [&](int g) { return gout + (int64_t)g * 720; });
         else
-          run_generated_level<6, false>(nsub, [&](int g) { return (const double*)Q + g * gen::kG6; },
-                                        [&](int g) { return P + g * gen::kS6; });
+          run_generated_static<6, false>([&](int g) { return (const double*)Q + g * gen::kG6; },
+                                         [&](int g) { return P + g * gen::kS6; });
       }
       if (K0 == 7) {
         // ---- level 7 as two register phases ---------------------------------------------------
@@ -425,8 +498,8 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
           run_generated_level<6, true>(nsub, [&](int g) { return gin + (int64_t)g * 720; },
                                        [&](int g) { return Q + g * gen::kG6; });
         else
-          run_generated_level<6, true>(nsub, [&](int g) { return (const double*)P + g * gen::kS6; },
-                                       [&](int g) { return Q + g * gen::kG6; });
+          run_generated_static<6, true>([&](int g) { return (const double*)P + g * gen::kS6; },
+                                        [&](int g) { return Q + g * gen::kG6; });
         __syncthreads();
       }
       if (K0 >= 5) {
@@ -434,6 +507,10 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
         if (K0 == 5)
           run_generated_level<5, true>(nsub, [&](int g) { return gin + (int64_t)g * 120; },
                                        [&](int g) { return P + g * gen::kG5; });
+        else if (K0 == 7)
+          run_generated_static<5, true>(
+              [&](int g) { return (const double*)Q + g * gen::kS5 + (g / 6) * gen::kP6; },
+              [&](int g) { return P + g * gen::kG5; });
         else
           run_generated_level<5, true>(
               nsub, [&](int g) { return (const double*)Q + g * gen::kS5 + (g / 6) * gen::kP6; },
