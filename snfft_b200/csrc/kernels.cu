@@ -310,6 +310,8 @@ constexpr ChunkTable<MAXT> make_chunk_table(int nseg, Count count, Cost cost) {
     }
   return T;
 }
+// (the tables are evaluated at compile time; reading the __device__ constexpr arrays there is fine)
+#pragma nv_diag_suppress 20091
 struct L5Count { constexpr int operator()(int p) const { return 42 * gen::kL5Dims[p]; } };
 struct L5Cost { constexpr int operator()(int p) const { return gen::kL5Dims[p]; } };
 struct L6Count { constexpr int operator()(int p) const { return 7 * gen::kL6Dims[p]; } };
@@ -318,6 +320,7 @@ struct P1Count { constexpr int operator()(int s) const { return gen::kL7P1SigmaS
 struct P1Cost { constexpr int operator()(int) const { return 1; } };
 struct P2Count { constexpr int operator()(int p) const { return gen::kL7P2MaxInst[p]; } };
 struct P2Cost { constexpr int operator()(int p) const { return gen::kL7PanelDim[p]; } };
+#pragma nv_diag_default 20091
 __device__ constexpr ChunkTable<24> kTabL5 = make_chunk_table<24>(gen::kL5Panels, L5Count{}, L5Cost{});
 __device__ constexpr ChunkTable<16> kTabL6 = make_chunk_table<16>(gen::kL6Panels, L6Count{}, L6Cost{});
 __device__ constexpr ChunkTable<16> kTabP1 = make_chunk_table<16>(7, P1Count{}, P1Cost{});
@@ -375,6 +378,57 @@ __device__ __forceinline__ void fused_level7_phase2(double* bufA, double* bufB, 
       kTabP2, [&](int panel, int inst) { gen::l7p2_panel<INV>(panel, inst, bufB, bufA, gspec); });
 }
 
+#ifdef SNFFT_PHASE_CLOCKS
+// debug build only: cycles between the barriers of the fused kernel, summed over CTAs (thread 0)
+__device__ unsigned long long g_phase_cycles[32];
+#define SNFFT_PH(i)                                                       \
+  if (K0 == 7 && threadIdx.x == 0) {                                      \
+    const long long now_ = clock64();                                     \
+    atomicAdd(&g_phase_cycles[(INV ? 16 : 0) + (i)], (unsigned long long)(now_ - last_)); \
+    last_ = now_;                                                         \
+  }
+#else
+#define SNFFT_PH(i)
+#endif
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Asynchronous stage-in of one S_7 group (K0 == 7) into Q + kFusedC (5040 doubles), issued while
+// the previous group is still in its last phases: in the forward direction Q is free behind the
+// C_5 rows once level 6 has read it, in the inverse once level 5 has.  Forward: the 16-byte chunks
+// of S_4 block b are rotated by b, so that the threads of the S_4 stage (one block each, 12
+// LDS.128) do not all hit the same two bank groups.
+template <bool INV>
+__device__ __forceinline__ void fused7_stage_async(double* Q, const double* gin) {
+  constexpr int kPer = (2520 + kFusedThreads - 1) / kFusedThreads;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int e = threadIdx.x + j * kFusedThreads;
+    if (e < 2520) {
+      int at = e;
+      if (!INV) {
+        const int b = e / 12, c = e - b * 12;
+        int pc = c + b % 12;
+        pc -= pc >= 12 ? 12 : 0;
+        at = b * 12 + pc;
+      }
+      cp_async16(Q + kFusedC + 2 * at, gin + 2 * e);
+    }
+  }
+}
+
 template <int K0, bool INV>
 __global__ void __launch_bounds__(kFusedThreads, 2)
 fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in may alias out
@@ -384,16 +438,25 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
   double* Q = sm + kFusedP;
   const int tid = threadIdx.x, nthreads = blockDim.x;
 
+  if (K0 == 7 && (int64_t)blockIdx.x < groups) {
+    fused7_stage_async<INV>(Q, in + (int64_t)blockIdx.x * S::kFact);
+    cp_async_wait_all();
+    __syncthreads();
+  }
   for (int64_t g0 = (int64_t)blockIdx.x * S::kGroups; g0 < groups; g0 += (int64_t)gridDim.x * S::kGroups) {
     const int ng = (int)min((int64_t)S::kGroups, groups - g0);
+    const int64_t gnext = g0 + (int64_t)gridDim.x * S::kGroups;  // this CTA's next chunk
+#ifdef SNFFT_PHASE_CLOCKS
+    long long last_ = clock64();
+#endif
     const double* gin = in + g0 * S::kFact;
     double* gout = out + g0 * S::kFact;
     const int n4 = ng * S::kS4Blocks;  // S_4 blocks in this chunk (<= 210)
     const int nelem = n4 * 24;
 #ifndef SNFFT_NO_L2_PREFETCH
     if (K0 == 7 && tid == 0) {
-      // the next group of this CTA is pulled into L2 while this one is transformed
-      const int64_t gn = g0 + (int64_t)gridDim.x * S::kGroups;
+      // the chunk after the next one is pulled into L2 (the next one is already being staged)
+      const int64_t gn = gnext + (int64_t)gridDim.x * S::kGroups;
       if (gn < groups)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + gn * S::kFact),
                      "r"(5040 * 8)
@@ -401,40 +464,40 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
     }
 #endif
     if (!INV) {
-      // ---- coalesced stage-in: S_4 blocks padded to stride kS4 ---------------------------------
-      if (K0 == 7) {
-        // all loads of the thread in flight before the first store (the group is 5040 doubles)
-        constexpr int kPer = (5040 + kFusedThreads - 1) / kFusedThreads;
-        double v[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = tid + j * kFusedThreads;
-          v[j] = e < 5040 ? __ldg(gin + e) : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = tid + j * kFusedThreads;
-          const int b = e / 24;
-          if (e < 5040) P[b * gen::kS4 + (e - b * 24)] = v[j];
-        }
-      } else {
+      // ---- coalesced stage-in: S_4 blocks padded to stride kS4 (K0 == 7: staged asynchronously) --
+      if (K0 != 7) {
         for (int e = tid; e < nelem; e += nthreads) {
           const int b = e / 24;
           P[b * gen::kS4 + (e - b * 24)] = gin[e];
         }
+        __syncthreads();
       }
-      __syncthreads();
+      SNFFT_PH(0)
       // ---- levels 2..4 in registers, in place ---------------------------------------------------
       if (tid < n4) {
         double r[24];
         double* blk = P + tid * gen::kS4;
+        if (K0 == 7) {
+          const double2* st = reinterpret_cast<const double2*>(Q + kFusedC) + tid * 12;
+          const int rot = tid % 12;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) r[i] = blk[i];
+          for (int c = 0; c < 12; ++c) {
+            int pc = c + rot;
+            pc -= pc >= 12 ? 12 : 0;
+            const double2 v = st[pc];
+            r[2 * c] = v.x;
+            r[2 * c + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) r[i] = blk[i];
+        }
         gen::s4_fwd(r);
 #pragma unroll
         for (int i = 0; i < 24; ++i) blk[i] = r[i];
       }
       __syncthreads();
+      SNFFT_PH(1)
       if (K0 == 4) {
         for (int e = tid; e < nelem; e += nthreads) {
           const int b = e / 24;
@@ -455,6 +518,7 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
       }
       if (K0 >= 6) {
         __syncthreads();
+        SNFFT_PH(2)
         const int nsub = n4 / 30;
         if (K0 == 6)
           run_generated_level<6, false>(nsub, [&](int g) { return (const double*)Q + g * gen::kG6; },
@@ -466,31 +530,24 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
       if (K0 == 7) {
         // ---- level 7 as two register phases ---------------------------------------------------
         __syncthreads();
+        SNFFT_PH(3)
+        if (gnext < groups) fused7_stage_async<false>(Q, in + gnext * S::kFact);
         fused_level7_phase1<false>(P, Q);
         __syncthreads();
+        SNFFT_PH(4)
         // finished rows go straight to global memory in runs of d_mu doubles (measured 5 % faster
         // than staging the spectrum in shared memory first; the inverse does stage its input)
         fused_level7_phase2<false>(P, Q, gout);
       }
     } else {
       if (K0 == 7) {
-        constexpr int kPer = (2520 + kFusedThreads - 1) / kFusedThreads;
-        double2 v[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = tid + j * kFusedThreads;
-          if (e < 2520) v[j] = __ldg(reinterpret_cast<const double2*>(gin) + e);
-        }
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = tid + j * kFusedThreads;
-          if (e < 2520) reinterpret_cast<double2*>(Q + kFusedC)[e] = v[j];
-        }
-        __syncthreads();
+        SNFFT_PH(5)
         fused_level7_phase2<true>(P, Q, Q + kFusedC);
         __syncthreads();
+        SNFFT_PH(6)
         fused_level7_phase1<true>(P, Q);
         __syncthreads();
+        SNFFT_PH(7)
       }
       if (K0 >= 6) {
         const int nsub = n4 / 30;
@@ -501,6 +558,7 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
           run_generated_static<6, true>([&](int g) { return (const double*)P + g * gen::kS6; },
                                         [&](int g) { return Q + g * gen::kG6; });
         __syncthreads();
+        SNFFT_PH(8)
       }
       if (K0 >= 5) {
         const int nsub = n4 / 5;
@@ -516,6 +574,8 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
               nsub, [&](int g) { return (const double*)Q + g * gen::kS5 + (g / 6) * gen::kP6; },
               [&](int g) { return P + g * gen::kG5; });
         __syncthreads();
+        SNFFT_PH(9)
+        if (K0 == 7 && gnext < groups) fused7_stage_async<true>(Q, in + gnext * S::kFact);
       }
       if (K0 == 4) {
         for (int e = tid; e < nelem; e += nthreads) {
@@ -523,6 +583,7 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
           P[b * gen::kS4 + (e - b * 24)] = gin[e];
         }
         __syncthreads();
+        SNFFT_PH(10)
       }
       if (tid < n4) {
         double r[24];
@@ -534,12 +595,15 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
         for (int i = 0; i < 24; ++i) blk[i] = r[i];
       }
       __syncthreads();
+      SNFFT_PH(11)
       for (int e = tid; e < nelem; e += nthreads) {
         const int b = e / 24;
         gout[e] = P[b * gen::kS4 + (e - b * 24)];
       }
     }
-    __syncthreads();  // buffers are reused by the next chunk
+    if (K0 == 7) cp_async_wait_all();  // the next chunk's input has landed
+    __syncthreads();                   // buffers are reused by the next chunk
+    SNFFT_PH(12)
   }
 }
 
@@ -817,7 +881,7 @@ __global__ void reorder_kernel(int n, Facts F, const uint32_t* __restrict__ tabl
 //   coset[top(A) + mid * S! + low] = lex[base(V, mid, low) + A],   A < R!, low < S!
 // i.e. every tile is a (S! x R!) transpose between 960-byte lexicographic runs and 192-byte
 // coset-major runs, both sector aligned (the element-wise gather above moves 16x the bytes).
-constexpr int kTileR = 5, kTileS = 4, kTileRF = 120, kTileSF = 24, kTileMinN = 9;
+constexpr int kTileR = 5, kTileRF = 120, kTileSF = 24, kTileMinN = 9;  // R = 5, S = 4
 constexpr int kTilePitch = kTileSF + 1;
 constexpr int kTileThreads = 256;
 
@@ -1321,3 +1385,9 @@ cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int
 }
 
 }  // namespace snfft
+
+#ifdef SNFFT_PHASE_CLOCKS
+extern "C" int snfft_debug_phase_cycles(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, snfft::g_phase_cycles, sizeof(unsigned long long) * 32);
+}
+#endif
