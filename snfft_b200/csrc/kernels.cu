@@ -391,11 +391,6 @@ __device__ unsigned long long g_phase_cycles[32];
 #define SNFFT_PH(i)
 #endif
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc)
