@@ -391,6 +391,11 @@ __device__ unsigned long long g_phase_cycles[32];
 #define SNFFT_PH(i)
 #endif
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc)
@@ -746,14 +751,16 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
     for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
       double* xs = xside + lg * P.in_stride + c0;
       double* ss = sside + lg * P.out_stride + c0;
-#pragma unroll 2
+      // all rows of the group in flight at once: global -> lane-private shared column, no registers
+#pragma unroll 4
       for (int r = 0; r < G.nrows; ++r) {
         const PhaseRow row = rows[r];
         const double* src = (INV && row.final) ? ss + row.dest : xs + row.xoff;
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc)
-          if (c0 + cc * 32 < pan.d) col[r * W + cc * 32] = src[cc * 32];
+          if (c0 + cc * 32 < pan.d) cp_async8(&col[r * W + cc * 32], src + cc * 32);
       }
+      cp_async_wait_all();  // a lane only reads what it copied itself
       for (int bi = 0; bi < G.nblk; ++bi) {
         const PhaseBlock b = blocks[INV ? G.nblk - 1 - bi : bi];
         const double* cmat = P.coef + (INV ? b.coef_i : b.coef_f);
