@@ -163,6 +163,18 @@ int snfft_shard_level_scratch(const snfft_shard* shard, int k, double* x_dev, do
 int snfft_shard_export_panel(const snfft_shard* shard, int k, int panel, int32_t* width, int64_t* dest,
                              int64_t* rowbase, int64_t* in_stride, int64_t* out_stride);
 
+/* The exchange as a pull over peer memory (NVLink P2P loads inside one kernel; no packing pass, no
+ * NCCL).  peer_bufs = host array of `world` device pointers that this process can dereference
+ * (CUDA IPC / symmetric memory; entry `rank` is the caller's own buffer).
+ *   inverse = 0: peer_bufs[r] = rank r's packed S_m spectra [its blocks][m!] after levels 2..m;
+ *                local_dev <- this rank's column shard [all blocks][size(rank, m)]
+ *   inverse = 1: peer_bufs[r] = rank r's column shard [all blocks][size(r, m)] after the inverse
+ *                levels n..m+1; local_dev <- this rank's packed S_m spectra [its blocks][m!]
+ * The caller orders the ranks around the call (every peer buffer complete before, none reused
+ * until every rank is done).  Replaces the Gather + sum of cube_ft.py:102-106 like the NCCL path. */
+int snfft_shard_exchange(snfft_shard* shard, const void* const* peer_bufs, void* local_dev, int inverse,
+                         void* stream);
+
 /* ---- Building blocks of the wreath-product transform (wreath.py / multi.py / cube_ft.py) -------
  * C[m,n] = A[m,k] B[k,n], fp64 row-major device matrices, on the DMMA tensor pipe
  * (mma.sync.m8n8k4.f64).  The direct sums sum_g f(g) rho(g) of multi.py:25-46 and the character

@@ -68,6 +68,7 @@ SIGNATURES = {
     "snfft_shard_level": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_shard_level_scratch": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_shard_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
+    "snfft_shard_exchange": (C.c_int, [_p, _p, _p, C.c_int, _p]),
     "snfft_dgemm": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _p]),
     "snfft_gather": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_plan_device_bytes": (C.c_int64, [_p]),

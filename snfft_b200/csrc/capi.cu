@@ -432,6 +432,8 @@ struct snfft_shard {
   std::vector<std::vector<int64_t>> size;  // size[q][k] = compact size of a level-k spectrum on rank q
   std::vector<ShardLevel> levels;          // levels[k], k = m+1..n, for `rank`
   std::vector<void*> allocs;
+  int32_t* pull_idx = nullptr;             // device: gather indices of all ranks, concatenated (lazy)
+  std::mutex pull_mutex;
 };
 
 namespace {
@@ -1052,6 +1054,51 @@ int snfft_shard_export_panel(const snfft_shard* sh, int k, int panel, int32_t* w
       if (dest) dest[s] = SL.dest[SL.slot_off[panel] + s];
       if (rowbase) rowbase[s] = SL.rowbase[SL.slot_off[panel] + s];
     }
+  });
+}
+
+int snfft_shard_exchange(snfft_shard* sh, const void* const* peer_bufs, void* local_dev, int inverse,
+                         void* stream) {
+  return guarded([&] {
+    if (!sh || !peer_bufs || !local_dev) throw InvalidArg("null argument");
+    if (sh->plan->device < 0) throw InvalidArg("host-only plan: no device exchange");
+    if (sh->world > kMaxWorld) throw InvalidArg("peer-memory exchange supports at most 16 ranks");
+    const HostPlan& host = sh->plan->host;
+    const auto& shapes = host.levels[sh->m].shapes;
+    DeviceGuard guard(sh->plan->device);
+    ShardPull X{};
+    X.rank = sh->rank;
+    X.world = sh->world;
+    X.mfact = host.fact[sh->m];
+    X.nblocks = host.fact[host.n] / host.fact[sh->m];
+    int64_t at = 0;
+    for (int r = 0; r < sh->world; ++r) {
+      if (!peer_bufs[r]) throw InvalidArg("null peer buffer");
+      X.peer[r] = static_cast<const double*>(peer_bufs[r]);
+      X.first[r] = shard_block_begin(X.nblocks, sh->world, r);
+      X.off[r] = (int32_t)at;
+      at += sh->size[r][sh->m];
+    }
+    X.first[sh->world] = X.nblocks;
+    X.off[sh->world] = (int32_t)at;
+    if (at != X.mfact) throw std::runtime_error("column shards do not tile the S_m spectrum");
+    {
+      std::lock_guard<std::mutex> lock(sh->pull_mutex);
+      if (!sh->pull_idx) {
+        std::vector<int32_t> idx;
+        idx.reserve((size_t)X.mfact);
+        for (int r = 0; r < sh->world; ++r)
+          for (size_t i = 0; i < shapes.size(); ++i) {
+            const int64_t d = shapes[i].dim;
+            for (int64_t u = 0; u < d; ++u)
+              for (int c = 0; c < sh->w[r][sh->m][i]; ++c)
+                idx.push_back((int32_t)(shapes[i].off + u * d + sh->first[r][i] + c));
+          }
+        sh->pull_idx = shard_upload(sh, idx);
+      }
+    }
+    X.idx = sh->pull_idx;
+    CUDA_OK(launch_shard_pull(X, static_cast<double*>(local_dev), inverse != 0, (cudaStream_t)stream));
   });
 }
 

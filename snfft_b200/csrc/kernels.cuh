@@ -54,6 +54,9 @@ cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int
 cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,
                           cudaStream_t stream);
 
+// the exchange of the sharded transform as P2P loads from peer memory (see ShardPull)
+cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, cudaStream_t stream);
+
 cudaError_t prepare_kernels();  // opt in to large dynamic shared memory (once per process)
 
 }  // namespace snfft

@@ -121,11 +121,14 @@ class ShardedPlan:
     def _local_inverse(self, blocks):
         return self.local_plan.inverse(blocks, 'coset')
 
-    def _level(self, k, x, inverse):
+    def _level(self, k, x, inverse, out=None):
         import torch
         groups = math.factorial(self.n) // math.factorial(k)
         size_out = self.sizes[self.rank][k - 1] * k if inverse else self.sizes[self.rank][k]
-        out = torch.empty(groups * size_out, dtype=torch.float64, device=x.device)
+        if out is None:
+            out = torch.empty(groups * size_out, dtype=torch.float64, device=x.device)
+        else:
+            out = out.reshape(-1)[:groups * size_out]
         # x is always an intermediate of this class, so the forward direction may overwrite it
         xs, ss = (out, x) if inverse else (x, out)
         with torch.cuda.device(self.device):
@@ -186,6 +189,8 @@ class ShardedPlan:
         """f_local: this rank's slice of the coset-major function (``local_elements()``).
         Returns the compact spectrum of this rank (use ``unpack`` / ``columns``)."""
         import torch
+        if getattr(self, '_p2p', None):
+            return self.forward_p2p(f_local)
         send = self.forward_local(f_local)
         mine = self.sizes[self.rank][self.m]
         recv = [torch.empty((eb - bb, mine), dtype=send[0].dtype, device=send[0].device)
@@ -213,12 +218,110 @@ class ShardedPlan:
     def inverse(self, compact):
         """Inverse of ``forward``: returns this rank's slice of the coset-major function."""
         import torch
+        if getattr(self, '_p2p', None):
+            return self.inverse_p2p(compact)
         send = self.inverse_local(compact)
         b, e = self.block_range[self.rank]
         recv = [torch.empty((e - b, self.sizes[q][self.m]), dtype=send[0].dtype, device=send[0].device)
                 for q in range(self.world)]
         self._exchange(send, recv)
         return self.inverse_finish(recv)
+
+    # ------------------------------------------------------------------ peer-memory exchange
+    # The same exchange as ONE kernel per direction that pulls straight from the peers' buffers
+    # over NVLink (snfft_shard_exchange): no packing / unpacking passes and no NCCL call.  The
+    # *_pull methods take device pointers that this process can dereference; `enable_p2p` gets
+    # them from torch's symmetric memory (one process per GPU) and makes forward / inverse use them.
+    def forward_local_spectra(self, f_local, out=None):
+        """Levels 2..m on this rank's blocks: packed S_m spectra [blocks, m!] (peer-readable if
+        `out` is a symmetric-memory buffer)."""
+        b, e = self.block_range[self.rank]
+        blocks = f_local.reshape(e - b, self.mfact)
+        if out is None:
+            return self.local_plan.forward(blocks, 'coset')
+        out = out.reshape(-1)[:(e - b) * self.mfact].reshape(e - b, self.mfact)
+        return self.local_plan.forward(blocks, 'coset', out=out)
+
+    def _pull(self, peer_ptrs, local, inverse):
+        import torch
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        with torch.cuda.device(self.device):
+            N.check(N.lib.snfft_shard_exchange(self._h, arr, N.ptr(local), int(inverse),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return local
+
+    def forward_finish_pull(self, peer_ptrs):
+        """peer_ptrs[r] = device pointer of rank r's `forward_local_spectra`; pulls this rank's
+        columns of every block and finishes levels m+1..n."""
+        import torch
+        x = torch.empty(self.nblocks * self.sizes[self.rank][self.m], dtype=torch.float64,
+                        device=torch.device('cuda', self.device))
+        self._pull(peer_ptrs, x, False)
+        for k in range(self.m + 1, self.n + 1):
+            x = self._level(k, x, False)
+        return x
+
+    def inverse_local_columns(self, compact, out=None):
+        """Levels n..m+1 backwards on my column shard: [all blocks, my columns] (peer-readable if
+        `out` is a symmetric-memory buffer)."""
+        x = compact
+        for k in range(self.n, self.m, -1):
+            x = self._level(k, x, True, out=out if k == self.m + 1 else None)
+        return x
+
+    def inverse_finish_pull(self, peer_ptrs):
+        """peer_ptrs[r] = device pointer of rank r's `inverse_local_columns`; pulls my blocks from
+        every rank's columns and runs levels m..2 backwards."""
+        import torch
+        b, e = self.block_range[self.rank]
+        local = torch.empty((e - b, self.mfact), dtype=torch.float64, device=torch.device('cuda', self.device))
+        self._pull(peer_ptrs, local, True)
+        return self._local_inverse(local).reshape(-1)
+
+    def enable_p2p(self):
+        """Allocate the two exchange buffers in symmetric memory and rendezvous (collective over
+        the group).  Returns False - and leaves the NCCL exchange in place - if this torch build or
+        this machine cannot map peer memory."""
+        import torch
+        import torch.distributed as dist
+        if getattr(self, '_p2p', None) is not None:
+            return True
+        if self.world == 1 or self.world > 16 or dist.get_backend(self.group) != 'nccl':
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            dev = torch.device('cuda', self.device)
+            nb = max(e - b for b, e in self.block_range)
+            wmax = max(self.sizes[r][self.m] for r in range(self.world))
+            spectra = symm.empty(nb * self.mfact, dtype=torch.float64, device=dev)
+            columns = symm.empty(self.nblocks * wmax, dtype=torch.float64, device=dev)
+            hs = symm.rendezvous(spectra, group)
+            hc = symm.rendezvous(columns, group)
+            self._p2p = dict(spectra=spectra, columns=columns, hs=hs, hc=hc,
+                             spectra_ptrs=[int(p) for p in hs.buffer_ptrs],
+                             columns_ptrs=[int(p) for p in hc.buffer_ptrs])
+        except Exception as exc:  # no symmetric memory here: keep the NCCL path
+            self._p2p = None
+            self._p2p_error = repr(exc)
+            return False
+        return True
+
+    def forward_p2p(self, f_local):
+        p = self._p2p
+        self.forward_local_spectra(f_local, out=p['spectra'])
+        p['hs'].barrier(channel=0)          # every rank's spectra are complete
+        x = self.forward_finish_pull(p['spectra_ptrs'])
+        p['hs'].barrier(channel=1)          # every rank has pulled: the buffer may be rewritten
+        return x
+
+    def inverse_p2p(self, compact):
+        p = self._p2p
+        self.inverse_local_columns(compact, out=p['columns'])
+        p['hc'].barrier(channel=0)
+        back = self.inverse_finish_pull(p['columns_ptrs'])
+        p['hc'].barrier(channel=1)
+        return back
 
     def gather_spectrum(self, compact):
         """Full packed spectrum assembled on every rank (for checks; moves the whole spectrum)."""

@@ -51,6 +51,30 @@ def test_virtual_world_on_one_gpu(n, world, split):
         assert ((back - coset[b:e]).norm() / coset[b:e].norm()).item() < 1e-10
 
 
+@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 3, 5), (9, 4, 7), (10, 8, 7), (10, 5, 8)])
+def test_peer_memory_exchange_on_one_gpu(n, world, split):
+    # the pull kernel (snfft_shard_exchange) with all ranks of a virtual world in one process:
+    # the peer pointers are ordinary device pointers here
+    nf = math.factorial(n)
+    coset = torch.randn(nf, dtype=torch.float64, device='cuda',
+                        generator=torch.Generator(device='cuda').manual_seed(n + world))
+    ranks = [ShardedPlan(n, r, world, device=0, split=split) for r in range(world)]
+    spectra = [sp.forward_local_spectra(coset[slice(*sp.local_elements())]) for sp in ranks]
+    ptrs = [t.data_ptr() for t in spectra]
+    compact = [sp.forward_finish_pull(ptrs) for sp in ranks]
+    # identical to the pack / hand-over / unpack path
+    sends = [sp.forward_local(coset[slice(*sp.local_elements())]) for sp in ranks]
+    for q, sp in enumerate(ranks):
+        want = sp.forward_finish([sends[r][q] for r in range(world)])
+        assert torch.equal(compact[q], want)
+    cols = [sp.inverse_local_columns(compact[q]) for q, sp in enumerate(ranks)]
+    ptrs = [t.data_ptr() for t in cols]
+    for r, sp in enumerate(ranks):
+        back = sp.inverse_finish_pull(ptrs)
+        b, e = sp.local_elements()
+        assert ((back - coset[b:e]).norm() / coset[b:e].norm()).item() < 1e-10
+
+
 def _nccl_worker(rank, world, n, port, ret):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -67,8 +91,16 @@ def _nccl_worker(rank, world, n, port, ret):
         full = sp.gather_spectrum(compact)
         want = get_plan(n, rank).forward(coset, 'coset')
         back = sp.inverse(compact)
+        # the same through the peer-memory exchange (symmetric memory), when this box can map it
+        p2p = sp.enable_p2p()
+        same = True
+        if p2p:
+            compact2 = sp.forward(coset[b:e].contiguous())
+            back2 = sp.inverse(compact2)
+            same = bool(torch.equal(compact2, compact)) and bool(torch.equal(back2, back))
         ret[rank] = (((full - want).norm() / want.norm()).item(),
-                     ((back - coset[b:e]).norm() / coset[b:e].norm()).item())
+                     ((back - coset[b:e]).norm() / coset[b:e].norm()).item(), p2p, same,
+                     getattr(sp, '_p2p_error', ''))
     finally:
         dist.destroy_process_group()
 
@@ -80,3 +112,5 @@ def test_nccl_two_gpus():
     mp.spawn(_nccl_worker, args=(2, 9, 29731, ret), nprocs=2, join=True)
     for rank in range(2):
         assert ret[rank][0] < 1e-10 and ret[rank][1] < 1e-10
+        assert ret[rank][3], 'peer-memory exchange differs from the NCCL exchange'
+    print('peer-memory exchange used:', ret[0][2], ret[0][4])
