@@ -173,6 +173,10 @@ def main():
         from snfft_b200.sharded import ShardedPlan
         batch = 1
         plan = ShardedPlan(n, rank, world, device=local)
+        # the exchange as one pull kernel over NVLink peer memory unless SNFFT_SHARD_EXCHANGE=nccl
+        exchange = 'nccl all_to_all'
+        if os.environ.get('SNFFT_SHARD_EXCHANGE', 'p2p') != 'nccl' and plan.enable_p2p():
+            exchange = 'peer-memory pull kernel (snfft_shard_exchange)'
         b, e = plan.local_elements()
         x = torch.randn(e - b, dtype=torch.float64, device=f'cuda:{local}', generator=gen)
         state = {}
@@ -311,7 +315,7 @@ def main():
                        'directions_per_step': 2, 'order': 'coset-major',
                        'l2': f'inputs {batch * nf * 8 / 1e6:.0f} MB per buffer, larger than the 126 MB L2'
                              if batch * nf * 8 > 126e6 else 'working set fits L2: not an HBM number',
-                       'parallelism': (f'coset-split column shards x{world}, one exchange' if sharded else
+                       'parallelism': (f'coset-split column shards x{world}, one exchange: {exchange}' if sharded else
                                        f'batch-replicas x{world}' if world > 1 else 'single GPU'),
                        'round_trip_rel_err': err},
             'roofline': roofline,
