@@ -752,7 +752,7 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
       double* xs = xside + lg * P.in_stride + c0;
       double* ss = sside + lg * P.out_stride + c0;
       // all rows of the group in flight at once: global -> lane-private shared column, no registers
-#pragma unroll 4
+#pragma unroll 8
       for (int r = 0; r < G.nrows; ++r) {
         const PhaseRow row = rows[r];
         const double* src = (INV && row.final) ? ss + row.dest : xs + row.xoff;
@@ -771,7 +771,7 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
           default: block_apply<5, CPL>(cmat, b.loc, col); break;
         }
       }
-#pragma unroll 2
+#pragma unroll 8
       for (int r = 0; r < G.nrows; ++r) {
         const PhaseRow row = rows[r];
         double* dst = (!INV && row.final) ? ss + row.dest : xs + row.xoff;
