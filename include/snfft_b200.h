@@ -163,15 +163,18 @@ int snfft_shard_level_scratch(const snfft_shard* shard, int k, double* x_dev, do
 int snfft_shard_export_panel(const snfft_shard* shard, int k, int panel, int32_t* width, int64_t* dest,
                              int64_t* rowbase, int64_t* in_stride, int64_t* out_stride);
 
-/* The exchange as a pull over peer memory (NVLink P2P loads inside one kernel; no packing pass, no
+/* The exchange over peer memory (NVLink P2P stores / loads inside one kernel; no packing pass, no
  * NCCL).  peer_bufs = host array of `world` device pointers that this process can dereference
- * (CUDA IPC / symmetric memory; entry `rank` is the caller's own buffer).
- *   inverse = 0: peer_bufs[r] = rank r's packed S_m spectra [its blocks][m!] after levels 2..m;
- *                local_dev <- this rank's column shard [all blocks][size(rank, m)]
- *   inverse = 1: peer_bufs[r] = rank r's column shard [all blocks][size(r, m)] after the inverse
- *                levels n..m+1; local_dev <- this rank's packed S_m spectra [its blocks][m!]
- * The caller orders the ranks around the call (every peer buffer complete before, none reused
- * until every rank is done).  Replaces the Gather + sum of cube_ft.py:102-106 like the NCCL path. */
+ * (CUDA IPC / symmetric memory; entry `rank` is the caller's own buffer): rank r's column-shard
+ * buffer [all blocks][size(r, m)].  local_dev = this rank's packed S_m spectra [its blocks][m!].
+ *   inverse = 0 (push): after levels 2..m, every rank writes the columns owned by rank r into
+ *                       rank r's column-shard buffer (contiguous remote runs of size(r, m) doubles);
+ *   inverse = 1 (pull): after the inverse levels n..m+1, every rank reads its blocks out of every
+ *                       rank's column-shard buffer into its packed spectra.
+ * The caller orders the ranks around the call (push: the destination buffers are free before and
+ * complete only after every rank has finished; pull: every peer buffer complete before, none
+ * reused until every rank is done).  Replaces the Gather + sum of cube_ft.py:102-106 like the
+ * NCCL path. */
 int snfft_shard_exchange(snfft_shard* shard, const void* const* peer_bufs, void* local_dev, int inverse,
                          void* stream);
 

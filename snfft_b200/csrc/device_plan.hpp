@@ -101,7 +101,7 @@ struct FusedDev {
 // Arguments of the peer-memory exchange of the sharded transform (kernels.cu: shard_pull_kernel)
 constexpr int kMaxWorld = 16;
 struct ShardPull {
-  const double* peer[kMaxWorld];  // per rank: its local spectra (forward) or its column shard (inverse)
+  const double* peer[kMaxWorld];  // per rank: its column-shard buffer [all blocks][size(r, m)]
   int64_t first[kMaxWorld + 1];   // first block of every rank; first[world] = number of blocks
   int32_t off[kMaxWorld + 1];     // idx[off[r] .. off[r+1]) = positions of rank r's columns in an S_m spectrum
   const int32_t* idx;             // device, m! entries

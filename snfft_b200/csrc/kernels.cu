@@ -1135,39 +1135,49 @@ __global__ void gather_kernel(const double* __restrict__ src, const int64_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// The one exchange of the sharded transform as a pull over peer memory (NVLink P2P loads): no
-// packing pass on the sender, no unpacking pass on the receiver, no NCCL.
-//   forward: cols[B][j] = peer[owner(B)].spectra[B - first[owner]][idx_q[j]]       (j < w_q)
-//   inverse: spectra[b][idx_r[j]] = peer[r].cols[first_q + b][j]                    (all r, j < w_r)
-// idx_r = positions of rank r's columns inside a packed S_m spectrum (snfft_shard_gather_index).
+// The one exchange of the sharded transform over peer memory (NVLink P2P inside one kernel): no
+// packing pass on the sender, no unpacking pass on the receiver, no NCCL.  Both directions walk
+// (own block b, position p of the concatenated per-rank column lists) and keep the REMOTE side
+// contiguous (runs of size(r, m) doubles per block), the scattered side local:
+//   forward (push): peer[r].cols[first_q + b][p - off[r]] = spectra[b][idx[p]]
+//   inverse (pull): spectra[b][idx[p]] = peer[r].cols[first_q + b][p - off[r]]
+// idx[off[r] .. off[r+1]) = positions of rank r's columns inside a packed S_m spectrum.
 // ---------------------------------------------------------------------------------------------
+constexpr int kPullUnroll = 4;
 template <bool INV>
 __global__ void __launch_bounds__(256)
-shard_pull_kernel(ShardPull X, double* __restrict__ local) {
-  if (!INV) {
-    // blockIdx.y = global block B; this rank's index list is idx[off[q] .. off[q+1])
-    const int q = X.rank;
-    const int32_t* __restrict__ idx = X.idx + X.off[q];
-    const int wq = X.off[q + 1] - X.off[q];
-    for (int64_t B = blockIdx.y; B < X.nblocks; B += gridDim.y) {
-      int r = 0;
-      while (r + 1 < X.world && B >= X.first[r + 1]) ++r;
-      const double* __restrict__ src = X.peer[r] + (B - X.first[r]) * X.mfact;
-      double* __restrict__ dst = local + B * wq;
-      for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < wq; j += gridDim.x * blockDim.x)
-        dst[j] = __ldg(src + idx[j]);
-    }
-  } else {
-    const int q = X.rank;
-    const int64_t nb = X.first[q + 1] - X.first[q];
-    for (int64_t b = blockIdx.y; b < nb; b += gridDim.y) {
-      double* __restrict__ dst = local + b * X.mfact;
-      for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < X.mfact; p += gridDim.x * blockDim.x) {
-        int r = 0;
-        while (r + 1 < X.world && p >= X.off[r + 1]) ++r;
-        const int wr = X.off[r + 1] - X.off[r];
-        dst[X.idx[p]] = __ldg(X.peer[r] + (X.first[q] + b) * wr + (p - X.off[r]));
+shard_exchange_kernel(ShardPull X, double* __restrict__ local) {
+  const int q = X.rank;
+  const int64_t nb = X.first[q + 1] - X.first[q];
+  const int stride = gridDim.x * blockDim.x;
+  for (int64_t b = blockIdx.y; b < nb; b += gridDim.y) {
+    double* __restrict__ spec = local + b * X.mfact;
+    const int64_t B = X.first[q] + b;
+    for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < X.mfact; p0 += stride * kPullUnroll) {
+      double v[kPullUnroll];
+      double* remote[kPullUnroll];
+      int at[kPullUnroll];
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int p = p0 + u * stride;
+        at[u] = -1;
+        if (p < X.mfact) {
+          int r = 0;
+          while (r + 1 < X.world && p >= X.off[r + 1]) ++r;
+          const int wr = X.off[r + 1] - X.off[r];
+          remote[u] = const_cast<double*>(X.peer[r]) + B * wr + (p - X.off[r]);
+          at[u] = X.idx[p];
+          v[u] = INV ? *remote[u] : spec[at[u]];
+        }
       }
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u)
+        if (at[u] >= 0) {
+          if (INV)
+            spec[at[u]] = v[u];
+          else
+            *remote[u] = v[u];
+        }
     }
   }
 }
@@ -1417,18 +1427,17 @@ cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, in
 
 cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, cudaStream_t stream) {
   const int q = X.rank;
-  const int64_t rows = inverse ? X.first[q + 1] - X.first[q] : X.nblocks;
-  const int64_t width = inverse ? X.mfact : X.off[q + 1] - X.off[q];
-  if (rows <= 0 || width <= 0) return cudaSuccess;
-  int64_t gx = (width + 255) / 256, gy = rows;
-  if (gx > 1024) gx = 1024;
+  const int64_t rows = X.first[q + 1] - X.first[q];
+  if (rows <= 0 || X.mfact <= 0) return cudaSuccess;
+  int64_t gx = (X.mfact + 256 * kPullUnroll - 1) / (256 * kPullUnroll), gy = rows;
+  if (gx > 256) gx = 256;
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)gx, (unsigned)gy);
   LaunchScope scope(kKindOther, stream);
   if (inverse)
-    shard_pull_kernel<true><<<grid, 256, 0, stream>>>(X, local);
+    shard_exchange_kernel<true><<<grid, 256, 0, stream>>>(X, local);
   else
-    shard_pull_kernel<false><<<grid, 256, 0, stream>>>(X, local);
+    shard_exchange_kernel<false><<<grid, 256, 0, stream>>>(X, local);
   return cudaGetLastError();
 }
 

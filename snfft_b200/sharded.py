@@ -228,60 +228,62 @@ class ShardedPlan:
         return self.inverse_finish(recv)
 
     # ------------------------------------------------------------------ peer-memory exchange
-    # The same exchange as ONE kernel per direction that pulls straight from the peers' buffers
-    # over NVLink (snfft_shard_exchange): no packing / unpacking passes and no NCCL call.  The
-    # *_pull methods take device pointers that this process can dereference; `enable_p2p` gets
-    # them from torch's symmetric memory (one process per GPU) and makes forward / inverse use them.
-    def forward_local_spectra(self, f_local, out=None):
-        """Levels 2..m on this rank's blocks: packed S_m spectra [blocks, m!] (peer-readable if
-        `out` is a symmetric-memory buffer)."""
-        b, e = self.block_range[self.rank]
-        blocks = f_local.reshape(e - b, self.mfact)
-        if out is None:
-            return self.local_plan.forward(blocks, 'coset')
-        out = out.reshape(-1)[:(e - b) * self.mfact].reshape(e - b, self.mfact)
-        return self.local_plan.forward(blocks, 'coset', out=out)
+    # The same exchange as ONE kernel per direction over NVLink peer memory (snfft_shard_exchange):
+    # forward = push (every rank stores rank r's columns of its blocks straight into rank r's
+    # column-shard buffer), inverse = pull (every rank loads its blocks out of every rank's
+    # column-shard buffer).  No packing / unpacking passes and no NCCL call; the remote side of
+    # both is contiguous.  The *_push / *_pull methods take device pointers that this process can
+    # dereference; `enable_p2p` gets them from torch's symmetric memory (one process per GPU) and
+    # makes forward / inverse use them.
+    def column_buffer_elements(self):
+        """Elements of a column-shard buffer that fits every rank (symmetric allocation)."""
+        return self.nblocks * max(self.sizes[r][self.m] for r in range(self.world))
 
-    def _pull(self, peer_ptrs, local, inverse):
+    def forward_local_spectra(self, f_local):
+        """Levels 2..m on this rank's blocks: packed S_m spectra [blocks, m!]."""
+        b, e = self.block_range[self.rank]
+        return self.local_plan.forward(f_local.reshape(e - b, self.mfact), 'coset')
+
+    def _exchange_kernel(self, peer_ptrs, local, inverse):
         import torch
         arr = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         with torch.cuda.device(self.device):
             N.check(N.lib.snfft_shard_exchange(self._h, arr, N.ptr(local), int(inverse),
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return local
 
-    def forward_finish_pull(self, peer_ptrs):
-        """peer_ptrs[r] = device pointer of rank r's `forward_local_spectra`; pulls this rank's
-        columns of every block and finishes levels m+1..n."""
-        import torch
-        x = torch.empty(self.nblocks * self.sizes[self.rank][self.m], dtype=torch.float64,
-                        device=torch.device('cuda', self.device))
-        self._pull(peer_ptrs, x, False)
+    def forward_push(self, spectra, peer_ptrs):
+        """peer_ptrs[r] = device pointer of rank r's column-shard buffer: stores rank r's columns of
+        my blocks there."""
+        self._exchange_kernel(peer_ptrs, spectra, False)
+
+    def forward_finish_columns(self, columns):
+        """columns = my column-shard buffer once every rank has pushed; levels m+1..n."""
+        x = columns.reshape(-1)[:self.nblocks * self.sizes[self.rank][self.m]]
         for k in range(self.m + 1, self.n + 1):
             x = self._level(k, x, False)
         return x
 
     def inverse_local_columns(self, compact, out=None):
-        """Levels n..m+1 backwards on my column shard: [all blocks, my columns] (peer-readable if
-        `out` is a symmetric-memory buffer)."""
+        """Levels n..m+1 backwards on my column shard: [all blocks, my columns], written into `out`
+        (my column-shard buffer) if given."""
         x = compact
         for k in range(self.n, self.m, -1):
             x = self._level(k, x, True, out=out if k == self.m + 1 else None)
         return x
 
     def inverse_finish_pull(self, peer_ptrs):
-        """peer_ptrs[r] = device pointer of rank r's `inverse_local_columns`; pulls my blocks from
-        every rank's columns and runs levels m..2 backwards."""
+        """peer_ptrs[r] = device pointer of rank r's column-shard buffer after its
+        `inverse_local_columns`; loads my blocks from every rank's columns, then levels m..2."""
         import torch
         b, e = self.block_range[self.rank]
         local = torch.empty((e - b, self.mfact), dtype=torch.float64, device=torch.device('cuda', self.device))
-        self._pull(peer_ptrs, local, True)
+        self._exchange_kernel(peer_ptrs, local, True)
         return self._local_inverse(local).reshape(-1)
 
     def enable_p2p(self):
-        """Allocate the two exchange buffers in symmetric memory and rendezvous (collective over
-        the group).  Returns False - and leaves the NCCL exchange in place - if this torch build or
-        this machine cannot map peer memory."""
+        """Allocate the column-shard exchange buffer in symmetric memory and rendezvous (collective
+        over the group).  Returns False - and leaves the NCCL exchange in place - if this torch
+        build or this machine cannot map peer memory."""
         import torch
         import torch.distributed as dist
         if getattr(self, '_p2p', None) is not None:
@@ -292,15 +294,9 @@ class ShardedPlan:
             import torch.distributed._symmetric_memory as symm
             group = self.group if self.group is not None else dist.group.WORLD
             dev = torch.device('cuda', self.device)
-            nb = max(e - b for b, e in self.block_range)
-            wmax = max(self.sizes[r][self.m] for r in range(self.world))
-            spectra = symm.empty(nb * self.mfact, dtype=torch.float64, device=dev)
-            columns = symm.empty(self.nblocks * wmax, dtype=torch.float64, device=dev)
-            hs = symm.rendezvous(spectra, group)
+            columns = symm.empty(self.column_buffer_elements(), dtype=torch.float64, device=dev)
             hc = symm.rendezvous(columns, group)
-            self._p2p = dict(spectra=spectra, columns=columns, hs=hs, hc=hc,
-                             spectra_ptrs=[int(p) for p in hs.buffer_ptrs],
-                             columns_ptrs=[int(p) for p in hc.buffer_ptrs])
+            self._p2p = dict(columns=columns, hc=hc, ptrs=[int(p) for p in hc.buffer_ptrs])
         except Exception as exc:  # no symmetric memory here: keep the NCCL path
             self._p2p = None
             self._p2p_error = repr(exc)
@@ -309,19 +305,21 @@ class ShardedPlan:
 
     def forward_p2p(self, f_local):
         p = self._p2p
-        self.forward_local_spectra(f_local, out=p['spectra'])
-        p['hs'].barrier(channel=0)          # every rank's spectra are complete
-        x = self.forward_finish_pull(p['spectra_ptrs'])
-        p['hs'].barrier(channel=1)          # every rank has pulled: the buffer may be rewritten
-        return x
+        spectra = self.forward_local_spectra(f_local)
+        p['hc'].barrier(channel=0)          # nobody still reads its column buffer
+        self.forward_push(spectra, p['ptrs'])
+        p['hc'].barrier(channel=1)          # every rank has pushed: my columns are complete
+        return self.forward_finish_columns(p['columns'])
 
     def inverse_p2p(self, compact):
         p = self._p2p
-        self.inverse_local_columns(compact, out=p['columns'])
-        p['hc'].barrier(channel=0)
-        back = self.inverse_finish_pull(p['columns_ptrs'])
-        p['hc'].barrier(channel=1)
-        return back
+        x = compact
+        for k in range(self.n, self.m + 1, -1):
+            x = self._level(k, x, True)
+        p['hc'].barrier(channel=0)          # nobody still pulls from my column buffer
+        self._level(self.m + 1, x, True, out=p['columns'])
+        p['hc'].barrier(channel=1)          # every rank's columns are complete
+        return self.inverse_finish_pull(p['ptrs'])
 
     def gather_spectrum(self, compact):
         """Full packed spectrum assembled on every rank (for checks; moves the whole spectrum)."""

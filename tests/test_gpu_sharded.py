@@ -53,22 +53,25 @@ def test_virtual_world_on_one_gpu(n, world, split):
 
 @pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 3, 5), (9, 4, 7), (10, 8, 7), (10, 5, 8)])
 def test_peer_memory_exchange_on_one_gpu(n, world, split):
-    # the pull kernel (snfft_shard_exchange) with all ranks of a virtual world in one process:
-    # the peer pointers are ordinary device pointers here
+    # the exchange kernel (snfft_shard_exchange: forward push, inverse pull) with all ranks of a
+    # virtual world in one process: the peer pointers are ordinary device pointers here
     nf = math.factorial(n)
     coset = torch.randn(nf, dtype=torch.float64, device='cuda',
                         generator=torch.Generator(device='cuda').manual_seed(n + world))
     ranks = [ShardedPlan(n, r, world, device=0, split=split) for r in range(world)]
-    spectra = [sp.forward_local_spectra(coset[slice(*sp.local_elements())]) for sp in ranks]
-    ptrs = [t.data_ptr() for t in spectra]
-    compact = [sp.forward_finish_pull(ptrs) for sp in ranks]
+    bufs = [torch.full((sp.column_buffer_elements(),), float('nan'), dtype=torch.float64, device='cuda')
+            for sp in ranks]
+    ptrs = [t.data_ptr() for t in bufs]
+    for sp in ranks:
+        sp.forward_push(sp.forward_local_spectra(coset[slice(*sp.local_elements())]), ptrs)
+    compact = [sp.forward_finish_columns(bufs[q]) for q, sp in enumerate(ranks)]
     # identical to the pack / hand-over / unpack path
     sends = [sp.forward_local(coset[slice(*sp.local_elements())]) for sp in ranks]
     for q, sp in enumerate(ranks):
         want = sp.forward_finish([sends[r][q] for r in range(world)])
         assert torch.equal(compact[q], want)
-    cols = [sp.inverse_local_columns(compact[q]) for q, sp in enumerate(ranks)]
-    ptrs = [t.data_ptr() for t in cols]
+    for q, sp in enumerate(ranks):
+        sp.inverse_local_columns(compact[q], out=bufs[q])
     for r, sp in enumerate(ranks):
         back = sp.inverse_finish_pull(ptrs)
         b, e = sp.local_elements()
