@@ -173,10 +173,10 @@ def main():
         from snfft_b200.sharded import ShardedPlan
         batch = 1
         plan = ShardedPlan(n, rank, world, device=local)
-        # the exchange as one pull kernel over NVLink peer memory unless SNFFT_SHARD_EXCHANGE=nccl
+        # the exchange as one kernel per direction over NVLink peer memory unless SNFFT_SHARD_EXCHANGE=nccl
         exchange = 'nccl all_to_all'
         if os.environ.get('SNFFT_SHARD_EXCHANGE', 'p2p') != 'nccl' and plan.enable_p2p():
-            exchange = 'peer-memory pull kernel (snfft_shard_exchange)'
+            exchange = 'peer-memory push/pull kernel (snfft_shard_exchange)'
         b, e = plan.local_elements()
         x = torch.randn(e - b, dtype=torch.float64, device=f'cuda:{local}', generator=gen)
         state = {}
