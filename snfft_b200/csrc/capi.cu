@@ -211,8 +211,29 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
     int64_t items = 0;
     int max_rows = 1;
     for (const PanelProgram& P : prog.panels) max_rows = std::max(max_rows, P.phases[ph].max_rows);
-    // more columns per lane amortise the per-block table loads; keep a warp's tile <= 12 KB
-    const int cpl = max_rows <= 12 ? 4 : (max_rows <= 24 ? 2 : 1);
+    // more columns per lane amortise the per-block table loads (measured 1.9 / 3.5 / 4.1 TB/s for
+    // 1 / 2 / 4 on wide panels); keep a warp's tile <= 12 KB, and on narrow panels (column shards)
+    // do not pay for lanes that have no column
+    const int cpl_max = max_rows <= 12 ? 4 : (max_rows <= 24 ? 2 : 1);
+    int cpl = 1;
+    {
+      const double speed[5] = {0, 0.5, 0.85, 0, 1.0};
+      double best = -1;
+      for (int c = 1; c <= cpl_max; c *= 2) {
+        double used = 0, paid = 0;
+        for (size_t p = 0; p < prog.panels.size(); ++p) {
+          const double rows = (double)prog.panels[p].phases[ph].rows.size();
+          const int w = lay.width[p];
+          used += rows * w;
+          paid += rows * ((w + 32 * c - 1) / (32 * c)) * 32 * c;
+        }
+        const double score = paid > 0 ? speed[c] * used / paid : 0;
+        if (score > best) {
+          best = score;
+          cpl = c;
+        }
+      }
+    }
     for (size_t p = 0; p < prog.panels.size(); ++p) {
       const PanelProgram& P = prog.panels[p];
       const PanelPhase& pp = P.phases[ph];
