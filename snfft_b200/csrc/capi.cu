@@ -241,6 +241,8 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
       PhasePanelDev pd;
       pd.d = w;
       pd.tiles = (w + 32 * cpl - 1) / (32 * cpl);
+      pd.pack = (w > 0 && w <= 16) ? 32 / w : 1;
+      pd.reserved = 0;
       pd.grp_off = (int32_t)groups.size();
       pd.ngroups = w > 0 ? (int32_t)pp.groups.size() : 0;
       pd.item_off = items;

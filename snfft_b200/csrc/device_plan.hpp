@@ -49,6 +49,8 @@ struct PhasePanelDev {
   int32_t grp_off;   // first group in PhaseDev::groups
   int32_t ngroups;
   int64_t item_off;  // prefix sum of ngroups * tiles
+  int32_t pack;      // narrow panels (d <= 16): floor(32 / d) members of the lg loop share a warp
+  int32_t reserved;
 };
 
 struct PhaseDev {

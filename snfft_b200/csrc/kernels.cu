@@ -744,11 +744,16 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
     const PhasePanelDev pan = P.panels[pi];
     const int64_t rem = item - pan.item_off;
     const int group = (int)(rem / pan.tiles), tile = (int)(rem - (int64_t)group * pan.tiles);
-    const int c0 = tile * W + lane;
+    // lane -> (member of the lg loop, column): one member per warp, or `pack` members side by side
+    // when the panel is at most 16 columns wide (column shards)
+    const int sub = pan.pack > 1 ? lane / pan.d : 0;
+    const int c0 = pan.pack > 1 ? lane - sub * pan.d : tile * W + lane;
     const PhaseGroup G = P.groups[pan.grp_off + group];
     const PhaseRow* __restrict__ rows = P.rows + G.row_off;
     const PhaseBlock* __restrict__ blocks = P.blocks + G.blk_off;
-    for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
+    for (int64_t lg0 = blockIdx.y; lg0 * pan.pack < lgroups; lg0 += gridDim.y) {
+      const int64_t lg = lg0 * pan.pack + sub;
+      const bool member = sub < pan.pack && lg < lgroups;
       double* xs = xside + lg * P.in_stride + c0;
       double* ss = sside + lg * P.out_stride + c0;
       // all rows of the group in flight at once: global -> lane-private shared column, no registers
@@ -758,7 +763,7 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
         const double* src = (INV && row.final) ? ss + row.dest : xs + row.xoff;
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc)
-          if (c0 + cc * 32 < pan.d) cp_async8(&col[r * W + cc * 32], src + cc * 32);
+          if (member && c0 + cc * 32 < pan.d) cp_async8(&col[r * W + cc * 32], src + cc * 32);
       }
       cp_async_wait_all();  // a lane only reads what it copied itself
       for (int bi = 0; bi < G.nblk; ++bi) {
@@ -777,7 +782,7 @@ phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside,
         double* dst = (!INV && row.final) ? ss + row.dest : xs + row.xoff;
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc)
-          if (c0 + cc * 32 < pan.d) dst[cc * 32] = col[r * W + cc * 32];
+          if (member && c0 + cc * 32 < pan.d) dst[cc * 32] = col[r * W + cc * 32];
       }
     }
   }
