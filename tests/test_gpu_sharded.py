@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 2, 7), (8, 3, 5), (9, 4, 7), (10, 8, 7)])
+@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 2, 7), (8, 3, 5), (9, 4, 7), (10, 8, 7), (9, 4, 8), (8, 3, None)])
 def test_virtual_world_on_one_gpu(n, world, split):
     nf = math.factorial(n)
     f = np.random.default_rng(n * 100 + world).standard_normal(nf)
@@ -51,7 +51,7 @@ def test_virtual_world_on_one_gpu(n, world, split):
         assert ((back - coset[b:e]).norm() / coset[b:e].norm()).item() < 1e-10
 
 
-@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 3, 5), (9, 4, 7), (10, 8, 7), (10, 5, 8)])
+@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 3, 5), (9, 4, 7), (10, 8, 7), (10, 5, 8), (9, 4, 8), (8, 3, 7)])
 def test_peer_memory_exchange_on_one_gpu(n, world, split):
     # the exchange kernel (snfft_shard_exchange: forward push, inverse pull) with all ranks of a
     # virtual world in one process: the peer pointers are ordinary device pointers here

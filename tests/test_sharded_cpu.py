@@ -105,7 +105,7 @@ def _worker(rank, world, n, split, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n,split', [(5, 3), (6, 4), (6, 5)])
+@pytest.mark.parametrize('n,split', [(5, 3), (6, 4), (6, 5), (5, 4)])
 def test_two_rank_sharded_transform_matches_oracle(n, split):
     world = 2
     mgr = mp.Manager()
