@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 2, 7), (8, 3, 5), (9, 4, 7), (10, 8, 7), (9, 4, 8), (8, 3, None)])
+@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 2, 7), (8, 3, 5), (9, 4, 7), (10, 8, 7), (9, 4, 8), (8, 3, 7)])
 def test_virtual_world_on_one_gpu(n, world, split):
     nf = math.factorial(n)
     f = np.random.default_rng(n * 100 + world).standard_normal(nf)
