@@ -94,6 +94,9 @@ constexpr int kThreads = 256;
 #ifndef SNFFT_FUSED_THREADS
 #define SNFFT_FUSED_THREADS 256
 #endif
+#ifndef SNFFT_FUSED_WAVES
+#define SNFFT_FUSED_WAVES 2
+#endif
 #ifndef SNFFT_L8_SUPER
 #define SNFFT_L8_SUPER 30
 #endif
@@ -1285,7 +1288,7 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
   const size_t smem = (size_t)(kFusedP + kFusedQ) * sizeof(double);
   const int64_t per_iter = FusedShape<K0>::kGroups;
   int64_t grid = (groups + per_iter - 1) / per_iter;
-  if (grid > 2LL * num_sms * 8) grid = 2LL * num_sms * 8;  // persistent beyond 8 waves
+  if (grid > 2LL * num_sms * SNFFT_FUSED_WAVES) grid = 2LL * num_sms * SNFFT_FUSED_WAVES;  // persistent beyond that
   LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
   if (inverse)
     fused_kernel<K0, true><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
