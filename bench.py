@@ -273,7 +273,9 @@ def main():
         else:
             # public host-buffer entry point: chunks pipelined over several streams so that H2D,
             # kernels and D2H overlap
-            plan.roundtrip_host(hx, hspec, hback, order='coset', chunks=16, streams=4)
+            plan.roundtrip_host(hx, hspec, hback, order='coset',
+                                chunks=int(os.environ.get('SNFFT_E2E_CHUNKS', 16)),
+                                streams=int(os.environ.get('SNFFT_E2E_STREAMS', 4)))
 
     e2e_step()
     barrier()
