@@ -161,6 +161,25 @@ def inverse_at(fhat, n, perms):
     return (out / math.factorial(n)).cpu().numpy()
 
 
+def cube2_inv_fft_part(irrep_dict, fourier_mat, coset_reps, cyclic_irrep_func, cyc_tup, perm_tup):
+    """One term of the wreath inverse at g = (cyc_tup, perm_tup) in C3 wr S_n (fft.py:158-172):
+    dim * trace(rho(g^-1) f_hat), with rho(g^-1) assembled from the block dictionary of
+    ``wreath.wreath_yor`` exactly as the reference's callers hold it (test_inv_fft.py:135).  The
+    caller sums over irreps and divides by the group order.  All elements at once on the device:
+    ``wreath.WreathPlan.inverse``."""
+    from .wreath import WreathCycSn, wreath_rep
+    cyc_inv, perm_inv = WreathCycSn.from_tup(cyc_tup, perm_tup, order=3).inv_tup_rep()
+    rho_inv = wreath_rep(cyc_inv, perm_inv, irrep_dict, coset_reps, cyclic_irrep_func)
+    return fourier_mat.shape[0] * np.sum(rho_inv.T * fourier_mat)
+
+
+def cube2_inv_fft_func(irrep_dict, fourier_mat, coset_reps, cyclic_irrep_func):
+    """(cyc_tup, perm_tup) -> ``cube2_inv_fft_part`` with the irrep fixed (fft.py:153-156)."""
+    def evaluate(cyc_tup, perm_tup):
+        return cube2_inv_fft_part(irrep_dict, fourier_mat, coset_reps, cyclic_irrep_func, cyc_tup, perm_tup)
+    return evaluate
+
+
 def _degree(size):
     n = 1
     while math.factorial(n) < size:

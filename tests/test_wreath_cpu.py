@@ -80,3 +80,29 @@ def test_homomorphism_with_orientations():
         assert np.allclose(lhs, W.wreath_rep(alpha, parts, o_gh, O.perm_mul(g, h)))
     ident = W.wreath_rep(alpha, parts, (0,) * 5, (1, 2, 3, 4, 5))
     assert np.allclose(ident, np.eye(ident.shape[0]))                      # test_wreath.py:76-85
+
+
+def test_cube2_inv_fft_part_matches_oracle_inverse():
+    # fft.py:153-172 / test_inv_fft.py:128-141: dim * tr(rho(g^-1) f_hat) per element.  The block
+    # dictionary comes from the oracle here (the mirror of wreath_yor needs the device), so this
+    # checks the host assembly: group inverse, cyclic scalars per coset, dense matrix, trace.
+    from snfft_b200 import fft as F
+    from snfft_b200 import wreath as MW
+    alpha, parts = CASES[1]
+    n = sum(alpha)
+    reps = W.coset_reps(n, alpha)
+    yy = W.young_yor(alpha, parts)
+    irrep_dict = {g: W.wreath_blocks(alpha, parts, g, reps, yy) for g in O.sn(n)}
+    oris = W.orientations(n)
+    rng = np.random.default_rng(3)
+    dim = len(reps) * next(iter(yy.values())).shape[0]
+    fhat = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    want = W.wreath_inverse_direct(alpha, parts, fhat, oris, 1)
+    rep_objs = [perm2.Perm2.from_tup(t) for t in reps]   # the reference holds Perm2 objects here
+    ift = F.cube2_inv_fft_func(irrep_dict, fhat, rep_objs, MW.cyclic_irreps(alpha))
+    perms = O.sn(n)
+    for r in (0, 7, 53, 119):
+        for q in (0, 5, len(oris) - 1):
+            got = ift(tuple(oris[q]), perms[r])
+            assert abs(got - want[r, q]) < 1e-9 * max(1.0, abs(want[r, q]))
+
