@@ -2,10 +2,17 @@
 //
 // Every level of the recursion (fft.py:96-112) is executed as the staged block program built by
 // plan.cpp: rows of a column block are combined by small dense blocks (2x2 .. 5x5), columns are
-// a passive, contiguous dimension.  Two drivers share the block executor:
-//   * fused_kernel  : levels 2..k0 (k0 <= 7) of one S_{k0} block entirely in shared memory, one
-//                     HBM read and one HBM write for k0-1 levels;
-//   * level_kernel  : one level k > k0, streaming column tiles of one panel through shared memory.
+// a passive, contiguous dimension.  The drivers:
+//   * fused_kernel         : levels 2..k0 (k0 <= 7) of one S_{k0} block entirely in shared memory
+//                            (generated register programs, gen_small.cuh), one HBM read and one
+//                            HBM write for k0-1 levels; the next block arrives by cp.async;
+//   * level8_kernel        : level 8 as two generated register phases per (panel, group chunk);
+//   * p1_inplace_kernel, p0_rows_kernel, phase_kernel : a level k >= 9 as in-place generated
+//                            stages 1..4 plus table-driven row-group phases for the later stages;
+//   * level_kernel         : any level, table-driven column tiles (snfft_level, tests);
+//   * reorder_tiled_kernel / reorder_kernel : lexicographic <-> coset-major element order;
+//   * shard_exchange_kernel: the one exchange of the multi-GPU transform over peer memory;
+//   * yor_kernel, dgemm_kernel (DMMA), gather_kernel : irrep matrices, direct sums, wreath stages.
 // fp64 has no tcgen05 kind, so the arithmetic is DFMA on the CUDA cores; the kernels are sized
 // against HBM (16 B per element per pass) and shared-memory bandwidth.
 #include "kernels.cuh"
