@@ -1084,7 +1084,7 @@ int snfft_shard_exchange(snfft_shard* sh, const void* const* peer_bufs, void* lo
                          void* stream) {
   return guarded([&] {
     if (!sh || !peer_bufs || !local_dev) throw InvalidArg("null argument");
-    if (sh->plan->device < 0) throw InvalidArg("host-only plan: no device exchange");
+    require_device(sh->plan);
     if (sh->world > kMaxWorld) throw InvalidArg("peer-memory exchange supports at most 16 ranks");
     const HostPlan& host = sh->plan->host;
     const auto& shapes = host.levels[sh->m].shapes;

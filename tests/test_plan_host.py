@@ -46,6 +46,14 @@ def test_host_only_plan_refuses_device_work():
     assert rc == 2 and b'no CPU fallback' in N.lib.snfft_last_error()
     assert N.lib.snfft_inverse(plan._h, N.ptr(buf), N.ptr(buf.copy()), N.ptr(buf.copy()), 1, 1, None) == 2
     assert N.lib.snfft_level(plan._h, 3, N.ptr(buf), N.ptr(buf.copy()), 4, 0, None) == 2
+    # the peer-memory exchange of a shard of a host-only plan: same refusal, and argument checks
+    shard = C.c_void_p()
+    assert N.lib.snfft_shard_create(plan._h, 0, 2, 3, C.byref(shard)) == 0
+    peers = (C.c_void_p * 2)(N.ptr(buf), N.ptr(buf))
+    assert N.lib.snfft_shard_exchange(shard, peers, N.ptr(buf), 0, None) == 2
+    assert N.lib.snfft_shard_exchange(shard, None, N.ptr(buf), 0, None) == 1
+    assert N.lib.snfft_shard_exchange(None, peers, N.ptr(buf), 0, None) == 1
+    N.lib.snfft_shard_destroy(shard)
 
 
 @pytest.mark.parametrize('n', range(1, 11))
