@@ -166,3 +166,42 @@ def test_operation_counts():
     assert abs(macs[0] - 2.0) < 1e-12 and all(b > a for a, b in zip(macs, macs[1:]))
     assert sum(macs) < 0.75 * 12 * 11          # below Maslen's (3/4) n (n-1) bound
     assert plan.macs_per_element(1) == 0.0 and plan.macs_per_element(13) == 0.0
+
+
+def test_reorder_tile_factorisation():
+    # The index identity behind reorder_tiled_kernel (kernels.cu), restated in Python and checked
+    # against the host coset-major -> lexicographic table: with the top R = 5 coset digits fixing
+    # the last 5 letters (an arrangement A of a value set V) and the first n-5 letters increasing,
+    #   c2l[top(A) + mid * 4! + low] = base(V, mid, low) + A
+    n, R, SF = 9, 5, 24
+    m = n - R
+    fact = [math.factorial(i) for i in range(n + 1)]
+    c2l = Plan(n, -1).coset_to_lex()
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        V = sorted(rng.choice(np.arange(1, n + 1), size=R, replace=False).tolist())
+        rest = [x for x in range(1, n + 1) if x not in V]          # iota: x-th value outside V
+        A = int(rng.integers(0, fact[R]))
+        # arrangement A of V (Lehmer decoding) = letters sigma(m+1..n)
+        pool, a, suf = list(V), A, []
+        for j in range(R):
+            q, a = divmod(a, fact[R - 1 - j])
+            suf.append(pool.pop(q))
+        # top coset digits: at level k the letter sits at (value - #extracted smaller values)
+        top = 0
+        for k in range(R - 1, -1, -1):
+            pos = suf[k] - sum(1 for t in range(k + 1, R) if suf[t] < suf[k])
+            top += (pos - 1) * fact[m + k]
+        mid = int(rng.integers(0, fact[m] // SF))
+        low = int(rng.integers(0, SF))
+        flat = mid * SF + low
+        q = list(range(n + 1))                                      # 1-based one-line notation
+        for k in range(m, 1, -1):
+            i = (flat // fact[k - 1]) % k + 1
+            q[i:k + 1] = q[i + 1:k + 1] + [q[i]]
+        base = 0
+        for a_ in range(1, m + 1):
+            smaller = rest[q[a_] - 1] - q[a_] + sum(1 for b in range(a_ + 1, m + 1) if q[b] < q[a_])
+            base += smaller * fact[n - a_]
+        assert c2l[top + flat] == base + A
+
