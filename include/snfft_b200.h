@@ -11,7 +11,10 @@
  *   - every function returns an int status (0 = OK); the message of the last failure on the
  *     calling thread is available from snfft_last_error(); nothing throws across the ABI;
  *   - device buffers are owned by the caller; a plan owns its tables and is immutable after
- *     creation, so concurrent calls on distinct streams are safe;
+ *     creation (two lazily built, mutex-guarded caches excepted: the generator tables of snfft_yor
+ *     and the matrix of snfft_dft_direct), so concurrent calls on distinct streams are safe;
+ *   - process-wide state is limited to three atomics: the launch counter (snfft_launch_count), the
+ *     timing switch (snfft_timing_enable) and the test hook snfft_debug_force_table_driven;
  *   - all device work is asynchronous on the stream that is passed (a cudaStream_t as void*);
  *   - there is no CPU fallback: calls that need a device fail with SNFFT_ERR_NO_DEVICE when the
  *     plan was created host-only (device = -1).
@@ -87,13 +90,15 @@ int snfft_yor_trans(const snfft_plan* plan, int k, int irrep, int j, double* out
 /* Forward transform f_hat(lambda) = sum_sigma f(sigma) rho_lambda(sigma) for every lambda |- n
  * (fft.py:16-37 `ft_full`, :72-113 `fft`, :39-70 `fft2`).  f_dev: double[batch][n!] in `order`;
  * fhat_dev: double[batch][n!] packed; work_dev: double[batch][n!] scratch (may alias neither).
- * f_dev is preserved. */
+ * f_dev is preserved.  All three buffers must be 16-byte aligned (the low levels stage their
+ * input with 16-byte asynchronous copies); a misaligned pointer is rejected with
+ * SNFFT_ERR_INVALID. */
 int snfft_forward(const snfft_plan* plan, const double* f_dev, double* fhat_dev, double* work_dev,
                   int64_t batch, int order, void* stream);
 
 /* Inverse transform f(sigma) = (1/n!) sum_lambda d_lambda tr(rho_lambda(sigma)^T f_hat(lambda))
  * (tile/par_inv_ft.py:27-45 evaluated for every sigma, by running the levels backwards).
- * fhat_dev is preserved. */
+ * fhat_dev is preserved.  Same 16-byte alignment requirement as snfft_forward. */
 int snfft_inverse(const snfft_plan* plan, const double* fhat_dev, double* f_dev, double* work_dev,
                   int64_t batch, int order, void* stream);
 
@@ -123,6 +128,8 @@ int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64
  * f_dev: lexicographic order. */
 int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, int64_t batch,
                      void* stream);
+/* Frees the matrix that snfft_dft_direct cached in the plan (synchronises the device first). */
+int snfft_dft_release(snfft_plan* plan);
 
 /* ---- Sharded transform (multi-GPU) ----------------------------------------------
  * The coset recursion of fft.py:96-98 splits S_n into n!/m! blocks of S_m (coset-major order puts
@@ -178,6 +185,39 @@ int snfft_shard_export_panel(const snfft_shard* shard, int k, int panel, int32_t
 int snfft_shard_exchange(snfft_shard* shard, const void* const* peer_bufs, void* local_dev, int inverse,
                          void* stream);
 
+/* The whole sharded transform of the calling rank in one call (SURVEY.md 8b `snfft_forward_sharded`):
+ * levels 2..m on its blocks, the peer-memory push, levels m+1..n on its column shard - all launched
+ * on `stream`, with device-side barriers between the ranks (flags in peer-accessible signal pads),
+ * no host synchronisation and no allocation.  Replaces the MPI driver of cube_ft.py:82-106.
+ * The workspace is owned by the caller and reused across calls:
+ *   peer_cols[r] : rank r's column-shard buffer, peer-accessible (CUDA IPC / symmetric memory),
+ *                  sizes[0] doubles on every rank;
+ *   peer_pads[r] : rank r's signal pad, peer-accessible, sizes[3] 8-byte words, zeroed once
+ *                  (by all ranks, before the first call of any rank);
+ *   local_a/b    : sizes[1] doubles each (this rank's S_m spectra and scratch), 16-byte aligned;
+ *   shard_a/b    : sizes[2] doubles each (intermediate levels of the column shard; may be NULL
+ *                  when n = m + 1);
+ *   status       : device int, zeroed once; set to 1 if a barrier gave up waiting for a peer (~2 s).
+ * f_local_dev: this rank's slice of the coset-major function (snfft_shard_blocks x m!, preserved);
+ * fhat_compact_dev: snfft_shard_size(rank, n) doubles, the compact spectrum of this rank.
+ * Every rank must make the same sequence of sharded calls. */
+typedef struct snfft_shard_ws {
+  void* peer_cols[16];
+  void* peer_pads[16];
+  void* local_a;
+  void* local_b;
+  void* shard_a;
+  void* shard_b;
+  int* status;
+} snfft_shard_ws;
+int snfft_shard_ws_sizes(const snfft_shard* shard, int64_t* sizes /* [4] */);
+int snfft_forward_sharded(snfft_shard* shard, const double* f_local_dev, double* fhat_compact_dev,
+                          const snfft_shard_ws* ws, void* stream);
+/* The inverse (fhat_compact_dev is preserved): levels n..m+1 backwards on the column shard, the
+ * peer-memory pull, levels m..2 backwards on this rank's blocks. */
+int snfft_inverse_sharded(snfft_shard* shard, const double* fhat_compact_dev, double* f_local_dev,
+                          const snfft_shard_ws* ws, void* stream);
+
 /* ---- Building blocks of the wreath-product transform (wreath.py / multi.py / cube_ft.py) -------
  * C[m,n] = A[m,k] B[k,n], fp64 row-major device matrices, on the DMMA tensor pipe
  * (mma.sync.m8n8k4.f64).  The direct sums sum_g f(g) rho(g) of multi.py:25-46 and the character
@@ -204,10 +244,13 @@ int64_t snfft_launch_count(void);
 int snfft_debug_force_table_driven(int on);
 
 /* Per-kernel timing for bench.py: when enabled, every launch of this library is bracketed by CUDA
- * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[8] and
- * launches_by_kind[8] (0 fused forward, 1 fused inverse, 2 level forward, 3 level inverse,
- * 4 reorder, 5 yor, 6 dgemm, 7 other) and resets the totals. */
-#define SNFFT_NUM_KERNEL_KINDS 8
+ * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[14] and
+ * launches_by_kind[14] and resets the totals.  Kinds: 0 fused forward (levels 2..7), 1 fused
+ * inverse, 2 level 8 forward (generated), 3 level 8 inverse, 4 table-driven level kernel,
+ * 5 in-place stages 1..4 of a level >= 9, 6 finished-row move of those levels, 7 row-group phase
+ * forward, 8 row-group phase inverse, 9 peer-memory exchange, 10 reorder, 11 yor, 12 dgemm,
+ * 13 other. */
+#define SNFFT_NUM_KERNEL_KINDS 14
 int snfft_timing_enable(int on);
 int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind);
 
@@ -223,6 +266,21 @@ int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_bloc
                        int32_t* block_m, int32_t* block_stage, int32_t* block_slots,
                        int32_t* block_final, double* coef_fwd, double* coef_inv, int64_t* dest,
                        int64_t* rowbase);
+
+/* Host-side export of the device tables of one row-group phase of level k >= 9 (phase >= 1; phase 0
+ * is stages 1..4, generated programs), so that CPU tests can interpret exactly what the phase
+ * kernel executes.  sizes int32[10] = {panels, bundles, rows, blocks, stage_first entries,
+ * columns per lane, stages, rows of the largest bundle, first stage, phases of the level}; the
+ * other buffers may be NULL to query sizes: panels int32[..][5] = {columns, tiles, first bundle,
+ * bundles, pack}; bundles int64[..][4] = {first row, first block, first stage_first entry, rows};
+ * rows int64[..][3] = {x-side offset, spectrum offset, finished flag}; blocks int32[..][8] =
+ * {row 0..4 (-1 padded, bundle-relative), m, forward coef offset, inverse coef offset};
+ * stage_first int32[bundles][stages][17]: per stage the block ranges of the 16 warps of a CTA
+ * (warp w runs blocks [w], [w+1]), bundle-relative). */
+int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes, int32_t* panels,
+                       int64_t* bundles, int64_t* rows, int32_t* blocks, int32_t* stage_first);
+/* The coefficient pool of level k that the block / phase tables index (doubles). */
+int snfft_export_coef(const snfft_plan* plan, int k, double* coef, int64_t* count);
 
 #ifdef __cplusplus
 }

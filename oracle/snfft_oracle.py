@@ -331,3 +331,72 @@ def unpack(packed, n):
     offs, dims = packed_layout(n)
     return {p: packed[..., offs[p]:offs[p] + dims[p] ** 2].reshape(packed.shape[:-1] + (dims[p], dims[p]))
             for p in partitions(n)}
+
+
+# --------------------------------------------------------------------------------------------
+# sparse forms for large shapes (n >= 10): the same generators without the dense d x d matrix
+# --------------------------------------------------------------------------------------------
+@lru_cache(maxsize=None)
+def yor_trans_sparse(partition, k):
+    """rho_lambda((k k+1)) as (diag, partner, offdiag) vectors: row i has ``diag[i]`` on the
+    diagonal and, when swapping k, k+1 in tableau i gives the standard tableau ``partner[i]``
+    (else -1), ``offdiag[i]`` in that column.  Same construction as ``yor_trans``
+    (yor.py:87-117, young_tableau.py:305-339), without materialising the matrix."""
+    tabs = tableaux(partition)
+    index = {t: i for i, t in enumerate(tabs)}
+    d = len(tabs)
+    diag = np.zeros(d)
+    partner = np.full(d, -1, dtype=np.int64)
+    off = np.zeros(d)
+    for i, t in enumerate(tabs):
+        c = _content_maps(t)
+        dist = c[k + 1] - c[k]
+        diag[i] = 1.0 / dist
+        swapped = tuple(tuple(k + 1 if x == k else (k if x == k + 1 else x) for x in row)
+                        for row in t)
+        j = index.get(swapped)
+        if j is not None:
+            partner[i] = j
+            off[i] = np.sqrt(1 - (1.0 / dist) ** 2)
+    return diag, partner, off
+
+
+def yor_word(tup):
+    """The generator word of sigma exactly as ``yor`` multiplies it (yor.py:52-85): for every
+    non-trivial cycle the reversed bubble-sort factors, cycles left to right.  Returns [a, ...]
+    meaning rho(sigma) = prod_a rho((a a+1))."""
+    n = len(tup)
+    word = []
+    for cyc in cycle_decomposition(tup):
+        word.extend(a for (a, _b) in cycle_to_adj_transpositions(cyc, n))
+    return word
+
+
+def yor_columns(partition, tup, cols):
+    """Columns ``cols`` of rho_lambda(sigma): the word of ``yor`` applied to unit vectors from
+    the right-most factor inwards, each factor as a 2-sparse row operation."""
+    d = len(tableaux(partition))
+    v = np.zeros((d, len(cols)))
+    v[list(cols), range(len(cols))] = 1.0
+    for a in reversed(yor_word(tup)):
+        diag, partner, off = yor_trans_sparse(partition, a)
+        has = partner >= 0
+        w = diag[:, None] * v
+        w[has] += off[has, None] * v[partner[has]]
+        v = w
+    return v
+
+
+def coset_index(tup):
+    """Position of sigma in coset-major order (the order in which the
+    recursion of fft.py:96-98 visits the group): sigma = c^(n)_{i_n} ... c^(2)_{i_2} with
+    c^(k)_i = (i i+1 ... k), i_k = (current sigma)(k); flat = sum_k (i_k - 1)(k-1)!."""
+    p = list(tup)
+    n = len(p)
+    flat = 0
+    for k in range(n, 1, -1):
+        i = p[k - 1]
+        flat += (i - 1) * math.factorial(k - 1)
+        # sigma <- (c^(k)_i)^-1 sigma: values above i move down by one, i goes to k (a fixed point)
+        p = [(v - 1 if v > i else (k if v == i else v)) for v in p[:k - 1]]
+    return flat

@@ -59,6 +59,7 @@ SIGNATURES = {
     "snfft_coset_to_lex_host": (C.c_int, [_p, _p]),
     "snfft_yor": (C.c_int, [_p, C.c_int, _p, C.c_int64, _p, _p]),
     "snfft_dft_direct": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
+    "snfft_dft_release": (C.c_int, [_p]),
     "snfft_shard_create": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "snfft_shard_destroy": (C.c_int, [_p]),
     "snfft_shard_blocks": (C.c_int, [_p, C.c_int, _p, _p]),
@@ -69,6 +70,9 @@ SIGNATURES = {
     "snfft_shard_level_scratch": (C.c_int, [_p, C.c_int, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_shard_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
     "snfft_shard_exchange": (C.c_int, [_p, _p, _p, C.c_int, _p]),
+    "snfft_shard_ws_sizes": (C.c_int, [_p, _p]),
+    "snfft_forward_sharded": (C.c_int, [_p, _p, _p, _p, _p]),
+    "snfft_inverse_sharded": (C.c_int, [_p, _p, _p, _p, _p]),
     "snfft_dgemm": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _p]),
     "snfft_gather": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_plan_device_bytes": (C.c_int64, [_p]),
@@ -78,12 +82,21 @@ SIGNATURES = {
     "snfft_timing_enable": (C.c_int, [C.c_int]),
     "snfft_timing_read": (C.c_int, [_p, _p]),
     "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "snfft_export_phase": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
+    "snfft_export_coef": (C.c_int, [_p, C.c_int, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)       # AttributeError here = header and library disagree
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+class ShardWorkspace(C.Structure):
+    """``snfft_shard_ws`` of include/snfft_b200.h."""
+    _fields_ = [("peer_cols", C.c_void_p * 16), ("peer_pads", C.c_void_p * 16),
+                ("local_a", C.c_void_p), ("local_b", C.c_void_p),
+                ("shard_a", C.c_void_p), ("shard_b", C.c_void_p), ("status", C.c_void_p)]
 
 
 def check(status: int) -> None:

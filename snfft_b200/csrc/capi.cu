@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -53,6 +54,13 @@ struct DeviceGuard {
   }
 };
 
+// device tables of one row-group phase plus the host copies the launcher needs
+struct PhaseHost {
+  BundleDev dev{};
+  std::vector<int32_t> items;  // per panel: bundles * tiles
+  std::vector<int32_t> pack;   // per panel
+};
+
 struct YorTables {
   int32_t* partner = nullptr;
   double* diag = nullptr;
@@ -71,11 +79,12 @@ struct snfft_plan {
   int ntiles[kMaxN + 1] = {};
   size_t level_smem[kMaxN + 1] = {};
   FusedDev fused;
-  std::vector<PhaseDev> phase_dev[kMaxN + 1];  // row-group phases of levels >= 9
+  std::vector<PhaseHost> phase_dev[kMaxN + 1];  // row-group phases of levels >= 9
   P1Dev p1_dev[kMaxN + 1] = {};                // generated in-place stages 1..4 of levels >= 9
   uint32_t* lex_table = nullptr;
   std::mutex lazy_mu;
   std::map<int, YorTables> yor_tables;
+  std::mutex dft_mu;             // guards dft_matrix (lazily built; released by snfft_dft_release)
   double* dft_matrix = nullptr;
 
   template <class T>
@@ -196,36 +205,55 @@ struct LevelLayout {
   std::vector<const uint32_t*> rowbase, dest;              // per panel: slot -> offset
   std::vector<int64_t> panel_off;                          // per panel: offset of the panel in a sub-spectrum
   int64_t in_stride = 0, out_stride = 0, block_stride = 0;  // group strides, distance between X_i blocks
+  int64_t lgroups_hint = 1;  // groups of the level in a whole transform of one function (n!/k!)
 };
+
+// Shared-memory budget of a phase CTA (default: two CTAs per SM); SNFFT_BUNDLE_KB overrides it for
+// experiments.
+int64_t bundle_smem_bytes() {
+  if (const char* env = std::getenv("SNFFT_BUNDLE_KB")) {
+    const int kb = std::atoi(env);
+    if (kb >= 16 && kb <= 224) return (int64_t)kb * 1024;
+  }
+  return 112 * 1024;
+}
+constexpr int kPhaseWarpsHost = 16;  // warps of a phase CTA (kernels.cu: kPhaseWarps)
 
 template <class Uploader>
 void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const double* coef, Uploader&& up,
-                      std::vector<PhaseDev>& out_devs) {
+                      std::vector<PhaseHost>& out_devs) {
   if (prog.panels.empty() || prog.panels[0].phases.empty()) return;
   const size_t nphases = prog.panels[0].phases.size();
-  for (size_t ph = 0; ph < nphases; ++ph) {
-    std::vector<PhasePanelDev> panels;
-    std::vector<PhaseGroup> groups;
-    std::vector<PhaseRow> rows;
-    std::vector<PhaseBlock> blocks;
-    int64_t items = 0;
-    int max_rows = 1;
-    for (const PanelProgram& P : prog.panels) max_rows = std::max(max_rows, P.phases[ph].max_rows);
-    // more columns per lane amortise the per-block table loads (measured 1.9 / 3.5 / 4.1 TB/s for
-    // 1 / 2 / 4 on wide panels); keep a warp's tile <= 12 KB, and on narrow panels (column shards)
-    // do not pay for lanes that have no column
-    const int cpl_max = max_rows <= 12 ? 4 : (max_rows <= 24 ? 2 : 1);
+  const int64_t kBundleSmemBytes = bundle_smem_bytes();
+  out_devs.push_back(PhaseHost{});  // phase 0 (stages 1..4) runs as generated programs: placeholder
+  for (size_t ph = 1; ph < nphases; ++ph) {
+    const int stage_lo = prog.panels[0].phases[ph].stage_lo, stage_hi = prog.panels[0].phases[ph].stage_hi;
+    const int nstages = stage_hi - stage_lo + 1;
+    int max_group = 1;
+    for (size_t p = 0; p < prog.panels.size(); ++p)
+      if (lay.width[p] > 0) max_group = std::max(max_group, prog.panels[p].phases[ph].max_rows);
+    // more columns per lane amortise the per-block descriptor and coefficient reads (the kernel is
+    // bound by its instruction count, not by HBM); the two tiles [rows of a bundle][32 * cpl columns]
+    // have to fit shared memory, and on narrow panels (column shards) lanes without a column are
+    // paid for
+    int cpl_max = 1;
+    while (cpl_max < 8 && (int64_t)max_group * 64 * cpl_max * 8 <= kBundleSmemBytes) cpl_max *= 2;
+    if ((int64_t)max_group * 32 * 8 > kBundleSmemBytes) throw std::runtime_error("phase group does not fit in shared memory");
     int cpl = 1;
     {
-      const double speed[5] = {0, 0.5, 0.85, 0, 1.0};
+      const double speed[9] = {0, 0.35, 0.55, 0, 0.8, 0, 0, 0, 1.0};
       double best = -1;
       for (int c = 1; c <= cpl_max; c *= 2) {
         double used = 0, paid = 0;
         for (size_t p = 0; p < prog.panels.size(); ++p) {
-          const double rows = (double)prog.panels[p].phases[ph].rows.size();
+          const double nr = (double)prog.panels[p].phases[ph].rows.size();
           const int w = lay.width[p];
-          used += rows * w;
-          paid += rows * ((w + 32 * c - 1) / (32 * c)) * 32 * c;
+          if (w == 0) continue;
+          const int W = 32 * c;
+          used += nr * w;
+          // narrow panels share a tile between members of the group loop when there are several
+          paid += (2 * w <= W && lay.lgroups_hint > 1) ? nr * w * ((double)W / (W / w * w))
+                                                       : nr * ((w + W - 1) / W) * W;
         }
         const double score = paid > 0 ? speed[c] * used / paid : 0;
         if (score > best) {
@@ -234,38 +262,132 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
         }
       }
     }
+    const int W = 32 * cpl;
+    const int cap_rows = (int)(kBundleSmemBytes / ((int64_t)W * 8));
+    std::vector<BundlePanelDev> panels;
+    std::vector<Bundle> bundles;
+    std::vector<uint32_t> row_xoff, row_dest;
+    std::vector<BundleBlock> blocks_f, blocks_i;
+    std::vector<uint32_t> stage_first;
+    int64_t items = 0;
+    int max_rows = 1;
     for (size_t p = 0; p < prog.panels.size(); ++p) {
       const PanelProgram& P = prog.panels[p];
       const PanelPhase& pp = P.phases[ph];
       const int w = lay.width[p];
-      PhasePanelDev pd;
+      BundlePanelDev pd;
       pd.d = w;
-      pd.tiles = (w + 32 * cpl - 1) / (32 * cpl);
-      pd.pack = (w > 0 && w <= 16) ? 32 / w : 1;
-      pd.reserved = 0;
-      pd.grp_off = (int32_t)groups.size();
-      pd.ngroups = w > 0 ? (int32_t)pp.groups.size() : 0;
+      pd.pack = (w > 0 && 2 * w <= W) ? W / w : 1;
+      pd.tiles = pd.pack > 1 ? 1 : (w + W - 1) / W;
+      pd.magic = w > 0 ? (65536 + w - 1) / w : 0;
+      pd.bundle_off = (int32_t)bundles.size();
+      pd.nbundles = 0;
       pd.item_off = items;
-      items += (int64_t)pd.ngroups * pd.tiles;
+      if (w > 0) {
+        size_t g = 0;
+        while (g < pp.groups.size()) {
+          // as many whole groups as fit the tile
+          size_t g1 = g;
+          int nr = 0;
+          while (g1 < pp.groups.size() && (g1 == g || nr + (int)pp.groups[g1].nrows <= cap_rows)) {
+            nr += (int)pp.groups[g1].nrows;
+            ++g1;
+          }
+          Bundle B;
+          B.row_off = (uint32_t)row_xoff.size();
+          B.blk_off = (uint32_t)blocks_f.size();
+          B.stage_off = (uint32_t)stage_first.size();
+          max_rows = std::max(max_rows, nr);
+          // rows of the bundle: those that stay on the x side first, then the ones finished in this
+          // phase (neither the load nor the store loop of the kernel selects a buffer per row)
+          std::vector<int> base(g1 - g);       // first row of every group in group order
+          std::vector<int> place((size_t)nr);  // group-order row -> position inside the bundle
+          {
+            int at = 0, nlow = 0;
+            for (size_t q = g; q < g1; ++q) {
+              const PhaseGroup& G = pp.groups[q];
+              base[q - g] = at;
+              for (uint32_t r = 0; r < G.nrows; ++r) nlow += pp.rows[G.row_off + r].final ? 0 : 1;
+              at += (int)G.nrows;
+            }
+            int lo_at = 0, hi_at = nlow;
+            at = 0;
+            row_xoff.resize(row_xoff.size() + nr);
+            row_dest.resize(row_dest.size() + nr);
+            for (size_t q = g; q < g1; ++q) {
+              const PhaseGroup& G = pp.groups[q];
+              for (uint32_t r = 0; r < G.nrows; ++r, ++at) {
+                const uint32_t slot = pp.row_slot[G.row_off + r];
+                const int pos = pp.rows[G.row_off + r].final ? hi_at++ : lo_at++;
+                place[at] = pos;
+                row_xoff[B.row_off + pos] = lay.rowbase[p][slot];
+                row_dest[B.row_off + pos] = lay.dest[p][slot];
+              }
+            }
+            B.nrows = (uint32_t)nr | ((uint32_t)nlow << 16);
+          }
+          uint32_t nb = 0;
+          for (int st = stage_lo; st <= stage_hi; ++st) {
+            // the blocks of the stage, sorted by (size, coefficient matrix): a warp works through a
+            // consecutive range and keeps the matrix in registers over a run of equal blocks
+            struct Item {
+              BundleBlock f;
+              uint32_t coef_i;
+            };
+            std::vector<Item> its;
+            for (size_t q = g; q < g1; ++q) {
+              const PhaseGroup& G = pp.groups[q];
+              for (uint32_t b = 0; b < G.nblk; ++b) {
+                const PhaseBlock& pb = pp.blocks[G.blk_off + b];
+                if (pb.stage != st) continue;
+                Item it{};
+                it.f.m = pb.m;
+                for (int a = 0; a < pb.m; ++a) it.f.loc[a] = (uint16_t)place[pb.loc[a] + base[q - g]];
+                it.f.coef = pb.coef_f;
+                it.coef_i = pb.coef_i;
+                its.push_back(it);
+              }
+            }
+            std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) {
+              return a.f.m != b.f.m ? a.f.m > b.f.m : a.f.coef < b.f.coef;
+            });
+            // ranges of the 16 warps, balanced by cost (m^2 multiply-adds + 2 m shared-memory accesses + overhead)
+            auto cost = [](const Item& it) { return (int64_t)it.f.m * it.f.m + 2 * it.f.m + 6; };
+            int64_t total = 0;
+            for (const Item& it : its) total += cost(it);
+            int64_t acc = 0;
+            size_t at2 = 0;
+            for (int w = 0; w < kPhaseWarpsHost; ++w) {
+              stage_first.push_back(nb + (uint32_t)at2);
+              const int64_t target = total * (w + 1) / kPhaseWarpsHost;
+              while (at2 < its.size() && acc + cost(its[at2]) / 2 < target) acc += cost(its[at2++]);
+            }
+            at2 = its.size();
+            for (const Item& it : its) {
+              BundleBlock bb = it.f;
+              blocks_f.push_back(bb);
+              bb.coef = it.coef_i;
+              blocks_i.push_back(bb);
+            }
+            nb += (uint32_t)its.size();
+            stage_first.push_back(nb);
+          }
+          bundles.push_back(B);
+          ++pd.nbundles;
+          g = g1;
+        }
+      }
+      items += (int64_t)pd.nbundles * pd.tiles;
       panels.push_back(pd);
-      if (w == 0) continue;
-      for (PhaseGroup g : pp.groups) {
-        g.row_off += (uint32_t)rows.size();
-        g.blk_off += (uint32_t)blocks.size();
-        groups.push_back(g);
-      }
-      for (size_t r = 0; r < pp.rows.size(); ++r) {
-        const uint32_t slot = pp.row_slot[r];
-        rows.push_back(PhaseRow{lay.rowbase[p][slot], lay.dest[p][slot], pp.rows[r].final});
-      }
-      blocks.insert(blocks.end(), pp.blocks.begin(), pp.blocks.end());
-      max_rows = std::max(max_rows, pp.max_rows);
     }
-    PhaseDev D;
+    BundleDev D;
     D.panels = up(panels);
-    D.groups = up(groups);
-    D.rows = up(rows);
-    D.blocks = up(blocks);
+    D.bundles = up(bundles);
+    D.row_xoff = up(row_xoff);
+    D.row_dest = up(row_dest);
+    D.blocks_f = up(blocks_f);
+    D.blocks_i = up(blocks_i);
+    D.stage_first = up(stage_first);
     D.coef = coef;
     D.nitems = items;
     D.in_stride = lay.in_stride;
@@ -273,7 +395,14 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const do
     D.npanels = (int32_t)panels.size();
     D.max_rows = max_rows;
     D.cols_per_lane = cpl;
-    out_devs.push_back(D);
+    D.nstages = nstages;
+    PhaseHost H;
+    H.dev = D;
+    for (const BundlePanelDev& pd : panels) {
+      H.items.push_back(pd.nbundles * pd.tiles);
+      H.pack.push_back(pd.pack);
+    }
+    out_devs.push_back(std::move(H));
   }
 }
 
@@ -329,6 +458,7 @@ LevelLayout plain_layout(const snfft_plan* plan, int k) {
   }
   lay.in_stride = lay.out_stride = plan->host.fact[k];
   lay.block_stride = plan->host.fact[k - 1];
+  lay.lgroups_hint = plan->host.fact[plan->host.n] / plan->host.fact[k];
   return lay;
 }
 
@@ -372,6 +502,12 @@ void require_device(const snfft_plan* plan) {
   if (plan->device < 0) throw NoDevice("plan was created host-only (device = -1); there is no CPU fallback");
 }
 
+// the fused kernel stages its input with 16-byte cp.async (kernels.cu: fused7_stage_async)
+void require_aligned16(const void* p, const char* name) {
+  if (reinterpret_cast<uintptr_t>(p) & 15)
+    throw InvalidArg(std::string(name) + " must be 16-byte aligned (a float64 view at an odd element offset is not)");
+}
+
 const ShapeInfo& shape_of(const snfft_plan* plan, int k, int irrep) {
   if (!plan) throw InvalidArg("plan is null");
   if (k < 1 || k > plan->host.n) throw InvalidArg("k out of range");
@@ -382,7 +518,7 @@ const ShapeInfo& shape_of(const snfft_plan* plan, int k, int irrep) {
 // Levels >= 9 inside snfft_forward / snfft_inverse: row-group phases.  xside = the buffer holding
 // the k sub-spectra per group (forward: the level's input, overwritten with intermediate rows;
 // inverse: the level's output), sside = the packed spectra of the level.
-void run_phases(const std::vector<PhaseDev>& phases, const P1Dev& p1, int num_sms, double* xside,
+void run_phases(const std::vector<PhaseHost>& phases, const P1Dev& p1, int num_sms, double* xside,
                 double* sside, int64_t groups, bool inverse, cudaStream_t stream);
 
 void run_level_phases(const snfft_plan* plan, int k, double* xside, double* sside, int64_t groups,
@@ -390,20 +526,23 @@ void run_level_phases(const snfft_plan* plan, int k, double* xside, double* ssid
   run_phases(plan->phase_dev[k], plan->p1_dev[k], plan->num_sms, xside, sside, groups, inverse, stream);
 }
 
-void run_phases(const std::vector<PhaseDev>& phases, const P1Dev& p1, int num_sms, double* xside,
+void run_phases(const std::vector<PhaseHost>& phases, const P1Dev& p1, int num_sms, double* xside,
                 double* sside, int64_t groups, bool inverse, cudaStream_t stream) {
   const int np = (int)phases.size();
   // phase 0 (stages 1..4) runs as generated in-place register programs, the others table-driven
   if (!inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, false, num_sms, stream));
   for (int i = 1; i < np; ++i)
-    CUDA_OK(launch_phase(phases[inverse ? np - i : i], xside, sside, groups, inverse, num_sms, stream));
+  {
+      const PhaseHost& H = phases[inverse ? np - i : i];
+      CUDA_OK(launch_phase(H.dev, H.items.data(), H.pack.data(), xside, sside, groups, inverse, num_sms, stream));
+    }
   if (inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, true, num_sms, stream));
 }
 
 void run_level(const snfft_plan* plan, int k, const double* in, double* out, int64_t groups,
                bool inverse, cudaStream_t stream) {
   CUDA_OK(launch_level(plan->level_dev[k], plan->tiles_dev[k], plan->ntiles[k], plan->level_smem[k],
-                       in, out, groups, inverse, plan->num_sms, stream));
+                       in, out, groups, inverse, g_force_table_driven.load(), plan->num_sms, stream));
 }
 
 YorTables& yor_tables_for(snfft_plan* plan, int irrep) {
@@ -442,7 +581,7 @@ struct ShardLevel {
   Tile* tiles_dev = nullptr;
   int ntiles = 0;
   size_t smem = 0;
-  std::vector<PhaseDev> phases;  // k >= 9: row-group phases on the shard's compact layout
+  std::vector<PhaseHost> phases;  // k >= 9: row-group phases on the shard's compact layout
   P1Dev p1 = {};
 };
 
@@ -457,6 +596,7 @@ struct snfft_shard {
   std::vector<void*> allocs;
   int32_t* pull_idx = nullptr;             // device: gather indices of all ranks, concatenated (lazy)
   std::mutex pull_mutex;
+  unsigned long long epoch[2] = {0, 0};    // barrier epochs per channel (every rank counts the same calls)
 };
 
 namespace {
@@ -569,6 +709,7 @@ void build_shard_level(snfft_shard* sh, int k) {
     lay.in_stride = L.in_stride;
     lay.out_stride = L.out_stride;
     lay.block_stride = s_in;
+    lay.lgroups_hint = host.fact[host.n] / host.fact[k];
     auto up = [&](const auto& v) { return shard_upload(sh, v); };
     build_phase_devs(prog, lay, L.coef, up, SL.phases);
     build_p1_dev(prog, lay, up, SL.p1);
@@ -636,6 +777,7 @@ int snfft_plan_destroy(snfft_plan* plan) {
     cudaGetDevice(&prev);
     cudaSetDevice(plan->device);
     for (void* p : plan->allocs) cudaFree(p);
+    if (plan->dft_matrix) cudaFree(plan->dft_matrix);
     if (prev >= 0) cudaSetDevice(prev);
   }
   delete plan;
@@ -692,98 +834,123 @@ int snfft_yor_trans(const snfft_plan* plan, int k, int irrep, int j, double* out
   });
 }
 
+namespace {
+
+// Levels 2..top of `batch` functions on S_top (top <= n; the same tables serve every top because in
+// coset-major order level k of the S_n transform IS level k of each of its S_top blocks).
+// f is preserved, the result lands in fhat, work is scratch.  lex: f is in lexicographic order
+// (top == n only).
+void forward_impl(const snfft_plan* plan, int top, const double* f_dev, double* fhat_dev, double* work_dev,
+                  int64_t batch, bool lex, cudaStream_t stream) {
+  const int k0 = top >= 4 ? std::min(top, kFusedMax) : 1;
+  const int64_t nf = plan->host.fact[top];
+  if (top == 1) {
+    CUDA_OK(cudaMemcpyAsync(fhat_dev, f_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  // passes: [fused 2..k0 if top >= 4] then one streaming pass per level k0+1..top.  Outputs alternate
+  // between work and fhat so that the last one lands in fhat; f is never written.
+  const int npasses = (k0 >= 4 ? 1 : 0) + (top - k0);
+  auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? fhat_dev : work_dev; };
+  const double* cur = f_dev;
+  if (lex) {
+    // reorder into the buffer the first pass does not write (a level pass cannot run in place)
+    double* tmp = out_of(0) == fhat_dev ? work_dev : fhat_dev;
+    CUDA_OK(launch_reorder(top, plan->lex_table, f_dev, tmp, batch, true, stream));
+    cur = tmp;
+  }
+  int pass = 0;
+  if (k0 >= 4) {
+    double* nxt = out_of(pass++);
+    FusedDev fused = plan->fused;
+    fused.k0 = k0;
+    fused.k0fact = (int32_t)plan->host.fact[k0];
+    CUDA_OK(launch_fused(fused, cur, nxt, batch * (nf / fused.k0fact), false, plan->num_sms, stream));
+    cur = nxt;
+  }
+  for (int k = k0 + 1; k <= top; ++k) {
+    double* nxt = out_of(pass++);
+    const int64_t groups = batch * (nf / plan->host.fact[k]);
+    if (!plan->phase_dev[k].empty() && !g_force_table_driven && cur != f_dev)
+      run_level_phases(plan, k, const_cast<double*>(cur), nxt, groups, false, stream);  // cur is scratch
+    else
+      run_level(plan, k, cur, nxt, groups, false, stream);
+    cur = nxt;
+  }
+}
+
+// The inverse of forward_impl: fhat is preserved, the result lands in f.
+void inverse_impl(const snfft_plan* plan, int top, const double* fhat_dev, double* f_dev, double* work_dev,
+                  int64_t batch, bool lex, cudaStream_t stream) {
+  const int k0 = top >= 4 ? std::min(top, kFusedMax) : 1;
+  const int64_t nf = plan->host.fact[top];
+  if (top == 1) {
+    CUDA_OK(cudaMemcpyAsync(f_dev, fhat_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  // passes: streaming levels top..k0+1, then the fused kernel (levels k0..2).  The last pass writes
+  // `target` (work when a reorder to lexicographic order follows, else f); earlier outputs
+  // alternate; fhat is never written.
+  const int npasses = (k0 >= 4 ? 1 : 0) + (top - k0);
+  double* target = lex ? work_dev : f_dev;
+  double* other = lex ? f_dev : work_dev;
+  auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? target : other; };
+  const double* cur = fhat_dev;
+  int pass = 0;
+  for (int k = top; k > k0; --k) {
+    double* nxt = out_of(pass++);
+    const int64_t groups = batch * (nf / plan->host.fact[k]);
+    if (!plan->phase_dev[k].empty() && !g_force_table_driven)
+      run_level_phases(plan, k, nxt, const_cast<double*>(cur), groups, true, stream);  // cur is only read
+    else
+      run_level(plan, k, cur, nxt, groups, true, stream);
+    cur = nxt;
+  }
+  if (k0 >= 4) {
+    double* nxt = out_of(pass++);
+    FusedDev fused = plan->fused;
+    fused.k0 = k0;
+    fused.k0fact = (int32_t)plan->host.fact[k0];
+    CUDA_OK(launch_fused(fused, cur, nxt, batch * (nf / fused.k0fact), true, plan->num_sms, stream));
+    cur = nxt;
+  }
+  if (lex) CUDA_OK(launch_reorder(top, plan->lex_table, work_dev, f_dev, batch, false, stream));
+}
+
+void check_transform_args(const snfft_plan* plan, const void* a, const void* b, const void* c, int64_t batch,
+                          int order) {
+  require_device(plan);
+  if (batch < 0) throw InvalidArg("batch < 0");
+  if (batch == 0) return;
+  if (!a || !b || !c) throw InvalidArg("null device buffer");
+  if (a == b || a == c || b == c) throw InvalidArg("f, fhat and work must be distinct buffers");
+  require_aligned16(a, "f_dev");
+  require_aligned16(b, "fhat_dev");
+  require_aligned16(c, "work_dev");
+  if (order != SNFFT_ORDER_COSET && order != SNFFT_ORDER_LEX) throw InvalidArg("bad order flag");
+}
+
+}  // namespace
+
 int snfft_forward(const snfft_plan* plan, const double* f_dev, double* fhat_dev, double* work_dev,
                   int64_t batch, int order, void* stream_) {
   return guarded([&] {
-    require_device(plan);
-    if (batch < 0) throw InvalidArg("batch < 0");
+    check_transform_args(plan, f_dev, fhat_dev, work_dev, batch, order);
     if (batch == 0) return;
-    if (!f_dev || !fhat_dev || !work_dev) throw InvalidArg("null device buffer");
-    if (f_dev == fhat_dev || f_dev == work_dev || fhat_dev == work_dev)
-      throw InvalidArg("f, fhat and work must be distinct buffers");
-    if (order != SNFFT_ORDER_COSET && order != SNFFT_ORDER_LEX) throw InvalidArg("bad order flag");
     DeviceGuard guard(plan->device);
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int n = plan->host.n, k0 = plan->fused.k0;
-    const int64_t nf = plan->host.fact[n];
-    if (n == 1) {
-      CUDA_OK(cudaMemcpyAsync(fhat_dev, f_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-      return;
-    }
-    // passes: [fused 2..k0 if n >= 4] then one streaming pass per level k0+1..n.  Outputs alternate
-    // between work and fhat so that the last one lands in fhat; f is never written.
-    const int npasses = (k0 >= 4 ? 1 : 0) + (n - k0);
-    auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? fhat_dev : work_dev; };
-    const double* cur = f_dev;
-    if (order == SNFFT_ORDER_LEX) {
-      // reorder into the buffer the first pass does not write (a level pass cannot run in place)
-      double* tmp = out_of(0) == fhat_dev ? work_dev : fhat_dev;
-      CUDA_OK(launch_reorder(n, plan->lex_table, f_dev, tmp, batch, true, stream));
-      cur = tmp;
-    }
-    int pass = 0;
-    if (k0 >= 4) {
-      double* nxt = out_of(pass++);
-      CUDA_OK(launch_fused(plan->fused, cur, nxt, batch * (nf / plan->fused.k0fact), false,
-                           plan->num_sms, stream));
-      cur = nxt;
-    }
-    for (int k = k0 + 1; k <= n; ++k) {
-      double* nxt = out_of(pass++);
-      const int64_t groups = batch * (nf / plan->host.fact[k]);
-      if (!plan->phase_dev[k].empty() && !g_force_table_driven && cur != f_dev)
-        run_level_phases(plan, k, const_cast<double*>(cur), nxt, groups, false, stream);  // cur is scratch
-      else
-        run_level(plan, k, cur, nxt, groups, false, stream);
-      cur = nxt;
-    }
+    forward_impl(plan, plan->host.n, f_dev, fhat_dev, work_dev, batch, order == SNFFT_ORDER_LEX,
+                 (cudaStream_t)stream_);
   });
 }
 
 int snfft_inverse(const snfft_plan* plan, const double* fhat_dev, double* f_dev, double* work_dev,
                   int64_t batch, int order, void* stream_) {
   return guarded([&] {
-    require_device(plan);
-    if (batch < 0) throw InvalidArg("batch < 0");
+    check_transform_args(plan, f_dev, fhat_dev, work_dev, batch, order);
     if (batch == 0) return;
-    if (!f_dev || !fhat_dev || !work_dev) throw InvalidArg("null device buffer");
-    if (f_dev == fhat_dev || f_dev == work_dev || fhat_dev == work_dev)
-      throw InvalidArg("f, fhat and work must be distinct buffers");
-    if (order != SNFFT_ORDER_COSET && order != SNFFT_ORDER_LEX) throw InvalidArg("bad order flag");
     DeviceGuard guard(plan->device);
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int n = plan->host.n, k0 = plan->fused.k0;
-    const int64_t nf = plan->host.fact[n];
-    if (n == 1) {
-      CUDA_OK(cudaMemcpyAsync(f_dev, fhat_dev, (size_t)batch * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-      return;
-    }
-    const bool lex = order == SNFFT_ORDER_LEX;
-    // passes: streaming levels n..k0+1, then the fused kernel (levels k0..2).  The last pass writes
-    // `target` (work when a reorder to lexicographic order follows, else f); earlier outputs
-    // alternate; fhat is never written.
-    const int npasses = (k0 >= 4 ? 1 : 0) + (n - k0);
-    double* target = lex ? work_dev : f_dev;
-    double* other = lex ? f_dev : work_dev;
-    auto out_of = [&](int pass) { return ((npasses - 1 - pass) % 2 == 0) ? target : other; };
-    const double* cur = fhat_dev;
-    int pass = 0;
-    for (int k = n; k > k0; --k) {
-      double* nxt = out_of(pass++);
-      const int64_t groups = batch * (nf / plan->host.fact[k]);
-      if (!plan->phase_dev[k].empty() && !g_force_table_driven)
-        run_level_phases(plan, k, nxt, const_cast<double*>(cur), groups, true, stream);  // cur is only read
-      else
-        run_level(plan, k, cur, nxt, groups, true, stream);
-      cur = nxt;
-    }
-    if (k0 >= 4) {
-      double* nxt = out_of(pass++);
-      CUDA_OK(launch_fused(plan->fused, cur, nxt, batch * (nf / plan->fused.k0fact), true,
-                           plan->num_sms, stream));
-      cur = nxt;
-    }
-    if (lex) CUDA_OK(launch_reorder(n, plan->lex_table, work_dev, f_dev, batch, false, stream));
+    inverse_impl(plan, plan->host.n, fhat_dev, f_dev, work_dev, batch, order == SNFFT_ORDER_LEX,
+                 (cudaStream_t)stream_);
   });
 }
 
@@ -829,11 +996,8 @@ int snfft_yor(const snfft_plan* plan_, int irrep, const int32_t* perms_dev, int6
     if (count == 0) return;
     if (!perms_dev || !out_dev) throw InvalidArg("null device buffer");
     DeviceGuard guard(plan->device);
-    if (plan->host.n == 1) {
-      std::vector<double> ones((size_t)count, 1.0);
-      CUDA_OK(cudaMemcpyAsync(out_dev, ones.data(), ones.size() * sizeof(double),
-                              cudaMemcpyHostToDevice, (cudaStream_t)stream));
-      CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (plan->host.n == 1) {  // rho((1)) = [1]: identity "word" on a 1 x 1 matrix, no tables needed
+      CUDA_OK(launch_yor(1, 1, nullptr, nullptr, perms_dev, count, out_dev, (cudaStream_t)stream));
       return;
     }
     YorTables& t = yor_tables_for(plan, irrep);
@@ -848,45 +1012,68 @@ int snfft_dft_direct(snfft_plan* plan, const double* f_dev, double* fhat_dev, in
     require_device(plan);
     const int n = plan->host.n;
     if (n > 8) throw InvalidArg("snfft_dft_direct supports n <= 8 (the [n!, n!] matrix is 13 GB at n = 8)");
-    if (batch < 0) throw InvalidArg("batch < 0");
+    if (batch < 0 || batch > 0x7fffffffLL) throw InvalidArg("batch out of range");
     if (batch == 0) return;
     if (!f_dev || !fhat_dev || f_dev == fhat_dev) throw InvalidArg("bad buffers");
     DeviceGuard guard(plan->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t nf = plan->host.fact[n];
-    if (!plan->dft_matrix) {
-      // R[sigma][packed (lambda,a,b)] = rho_lambda(sigma)[a][b], sigma in lexicographic order
-      std::vector<int32_t> perms((size_t)nf * n);
-      std::vector<int> p(n);
-      for (int i = 0; i < n; ++i) p[i] = i + 1;
-      int64_t r = 0;
-      do {
-        for (int i = 0; i < n; ++i) perms[r * n + i] = p[i];
-        ++r;
-      } while (std::next_permutation(p.begin(), p.end()));
-      int32_t* perms_dev = nullptr;
-      double* tmp = nullptr;
-      CUDA_OK(cudaMalloc((void**)&perms_dev, perms.size() * sizeof(int32_t)));
-      CUDA_OK(cudaMemcpy(perms_dev, perms.data(), perms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-      double* R = (double*)plan->alloc((size_t)nf * nf * sizeof(double));
-      int64_t dmax = 0;
-      for (const ShapeInfo& s : plan->host.levels[n].shapes) dmax = std::max(dmax, s.dim);
-      CUDA_OK(cudaMalloc((void**)&tmp, (size_t)nf * dmax * dmax * sizeof(double)));
-      for (size_t irrep = 0; irrep < plan->host.levels[n].shapes.size(); ++irrep) {
-        const ShapeInfo& s = plan->host.levels[n].shapes[irrep];
-        const int rc = snfft_yor(plan, (int)irrep, perms_dev, nf, tmp, stream);
-        if (rc != SNFFT_OK) throw CudaError(g_last_error);
-        CUDA_OK(cudaMemcpy2DAsync(R + s.off, (size_t)nf * sizeof(double), tmp,
-                                  (size_t)(s.dim * s.dim) * sizeof(double),
-                                  (size_t)(s.dim * s.dim) * sizeof(double), (size_t)nf,
-                                  cudaMemcpyDeviceToDevice, stream));
+    const double* matrix = nullptr;
+    {
+      // the matrix is built once per plan, on first use (like the yor tables: guarded by lazy_mu)
+      std::lock_guard<std::mutex> lock(plan->dft_mu);
+      if (!plan->dft_matrix) {
+        // R[sigma][packed (lambda,a,b)] = rho_lambda(sigma)[a][b], sigma in lexicographic order
+        std::vector<int32_t> perms((size_t)nf * n);
+        std::vector<int> p(n);
+        for (int i = 0; i < n; ++i) p[i] = i + 1;
+        int64_t r = 0;
+        do {
+          for (int i = 0; i < n; ++i) perms[r * n + i] = p[i];
+          ++r;
+        } while (std::next_permutation(p.begin(), p.end()));
+        struct Scratch {  // freed on every exit path
+          void* p = nullptr;
+          ~Scratch() { if (p) cudaFree(p); }
+        } perms_dev, tmp, R;
+        CUDA_OK(cudaMalloc(&perms_dev.p, perms.size() * sizeof(int32_t)));
+        CUDA_OK(cudaMemcpy(perms_dev.p, perms.data(), perms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&R.p, (size_t)nf * nf * sizeof(double)));
+        int64_t dmax = 0;
+        for (const ShapeInfo& s : plan->host.levels[n].shapes) dmax = std::max(dmax, s.dim);
+        CUDA_OK(cudaMalloc(&tmp.p, (size_t)nf * dmax * dmax * sizeof(double)));
+        for (size_t irrep = 0; irrep < plan->host.levels[n].shapes.size(); ++irrep) {
+          const ShapeInfo& s = plan->host.levels[n].shapes[irrep];
+          const int rc = snfft_yor(plan, (int)irrep, (const int32_t*)perms_dev.p, nf, (double*)tmp.p, stream);
+          if (rc != SNFFT_OK) throw CudaError(g_last_error);
+          CUDA_OK(cudaMemcpy2DAsync((double*)R.p + s.off, (size_t)nf * sizeof(double), tmp.p,
+                                    (size_t)(s.dim * s.dim) * sizeof(double),
+                                    (size_t)(s.dim * s.dim) * sizeof(double), (size_t)nf,
+                                    cudaMemcpyDeviceToDevice, stream));
+        }
+        CUDA_OK(cudaStreamSynchronize(stream));
+        plan->dft_matrix = (double*)R.p;
+        plan->device_bytes += (int64_t)((size_t)nf * nf * sizeof(double));
+        R.p = nullptr;  // owned by the plan from here on (snfft_dft_release / snfft_plan_destroy)
       }
-      CUDA_OK(cudaStreamSynchronize(stream));
-      cudaFree(tmp);
-      cudaFree(perms_dev);
-      plan->dft_matrix = R;
+      matrix = plan->dft_matrix;
     }
-    CUDA_OK(launch_dgemm(f_dev, plan->dft_matrix, fhat_dev, (int)batch, (int)nf, (int)nf, stream));
+    CUDA_OK(launch_dgemm(f_dev, matrix, fhat_dev, (int)batch, (int)nf, (int)nf, stream));
+  });
+}
+
+int snfft_dft_release(snfft_plan* plan) {
+  return guarded([&] {
+    if (!plan) throw InvalidArg("plan is null");
+    std::lock_guard<std::mutex> lock(plan->dft_mu);
+    if (plan->dft_matrix) {
+      DeviceGuard guard(plan->device);
+      const int64_t nf = plan->host.fact[plan->host.n];
+      CUDA_OK(cudaDeviceSynchronize());
+      cudaFree(plan->dft_matrix);
+      plan->device_bytes -= (int64_t)((size_t)nf * nf * sizeof(double));
+      plan->dft_matrix = nullptr;
+    }
   });
 }
 
@@ -1028,12 +1215,9 @@ int snfft_shard_level(const snfft_shard* sh, int k, const double* in_dev, double
     if (groups < 0) throw InvalidArg("groups < 0");
     DeviceGuard guard(sh->plan->device);
     const ShardLevel& SL = sh->levels[k];
-    const bool saved = g_force_table_driven;
-    g_force_table_driven = true;  // the generated level-8 programs assume the full column pitch
-    cudaError_t e = launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, in_dev, out_dev, groups,
-                                 inverse != 0, sh->plan->num_sms, (cudaStream_t)stream);
-    g_force_table_driven = saved;
-    CUDA_OK(e);
+    // always table-driven: the generated level-8 programs assume the full column pitch
+    CUDA_OK(launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, in_dev, out_dev, groups, inverse != 0,
+                         true, sh->plan->num_sms, (cudaStream_t)stream));
   });
 }
 
@@ -1051,14 +1235,10 @@ int snfft_shard_level_scratch(const snfft_shard* sh, int k, double* x_dev, doubl
       run_phases(SL.phases, SL.p1, sh->plan->num_sms, x_dev, s_dev, groups, inverse != 0, (cudaStream_t)stream);
       return;
     }
-    const bool saved = g_force_table_driven;
-    g_force_table_driven = true;
-    cudaError_t e = inverse ? launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, s_dev, x_dev, groups, true,
-                                           sh->plan->num_sms, (cudaStream_t)stream)
-                            : launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, x_dev, s_dev, groups, false,
-                                           sh->plan->num_sms, (cudaStream_t)stream);
-    g_force_table_driven = saved;
-    CUDA_OK(e);
+    CUDA_OK(inverse ? launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, s_dev, x_dev, groups, true, true,
+                                   sh->plan->num_sms, (cudaStream_t)stream)
+                    : launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, x_dev, s_dev, groups, false, true,
+                                   sh->plan->num_sms, (cudaStream_t)stream));
   });
 }
 
@@ -1080,48 +1260,176 @@ int snfft_shard_export_panel(const snfft_shard* sh, int k, int panel, int32_t* w
   });
 }
 
+namespace {
+
+void shard_exchange_impl(snfft_shard* sh, const void* const* peer_bufs, void* local_dev, bool inverse,
+                         cudaStream_t stream) {
+  if (sh->world > kMaxWorld) throw InvalidArg("peer-memory exchange supports at most 16 ranks");
+  const HostPlan& host = sh->plan->host;
+  const auto& shapes = host.levels[sh->m].shapes;
+  ShardPull X{};
+  X.rank = sh->rank;
+  X.world = sh->world;
+  X.mfact = host.fact[sh->m];
+  X.nblocks = host.fact[host.n] / host.fact[sh->m];
+  int64_t at = 0;
+  for (int r = 0; r < sh->world; ++r) {
+    if (!peer_bufs[r]) throw InvalidArg("null peer buffer");
+    X.peer[r] = static_cast<const double*>(peer_bufs[r]);
+    X.first[r] = shard_block_begin(X.nblocks, sh->world, r);
+    X.off[r] = (int32_t)at;
+    at += sh->size[r][sh->m];
+  }
+  X.first[sh->world] = X.nblocks;
+  X.off[sh->world] = (int32_t)at;
+  if (at != X.mfact) throw std::runtime_error("column shards do not tile the S_m spectrum");
+  {
+    std::lock_guard<std::mutex> lock(sh->pull_mutex);
+    if (!sh->pull_idx) {
+      std::vector<int32_t> idx;
+      idx.reserve((size_t)X.mfact);
+      for (int r = 0; r < sh->world; ++r)
+        for (size_t i = 0; i < shapes.size(); ++i) {
+          const int64_t d = shapes[i].dim;
+          for (int64_t u = 0; u < d; ++u)
+            for (int c = 0; c < sh->w[r][sh->m][i]; ++c)
+              idx.push_back((int32_t)(shapes[i].off + u * d + sh->first[r][i] + c));
+        }
+      sh->pull_idx = shard_upload(sh, idx);
+    }
+  }
+  X.idx = sh->pull_idx;
+  CUDA_OK(launch_shard_pull(X, static_cast<double*>(local_dev), inverse, stream));
+}
+
+// one level m < k <= n on the calling rank's column shard (x side may be overwritten going forward)
+void shard_level_impl(const snfft_shard* sh, int k, double* x_dev, double* s_dev, bool inverse, cudaStream_t stream) {
+  const HostPlan& host = sh->plan->host;
+  const int64_t groups = host.fact[host.n] / host.fact[k];
+  const ShardLevel& SL = sh->levels[k];
+  if (!SL.phases.empty() && !g_force_table_driven) {
+    run_phases(SL.phases, SL.p1, sh->plan->num_sms, x_dev, s_dev, groups, inverse, stream);
+    return;
+  }
+  CUDA_OK(inverse ? launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, s_dev, x_dev, groups, true, true,
+                                 sh->plan->num_sms, stream)
+                  : launch_level(SL.dev, SL.tiles_dev, SL.ntiles, SL.smem, x_dev, s_dev, groups, false, true,
+                                 sh->plan->num_sms, stream));
+}
+
+void shard_barrier(snfft_shard* sh, const snfft_shard_ws* ws, int channel, cudaStream_t stream) {
+  ShardBarrier Bq{};
+  for (int r = 0; r < sh->world; ++r) {
+    if (!ws->peer_pads[r]) throw InvalidArg("null signal pad");
+    Bq.pads[r] = static_cast<unsigned long long*>(ws->peer_pads[r]);
+  }
+  Bq.epoch = ++sh->epoch[channel];
+  Bq.status = ws->status;
+  Bq.rank = sh->rank;
+  Bq.world = sh->world;
+  Bq.channel = channel;
+  CUDA_OK(launch_shard_barrier(Bq, stream));
+}
+
+void check_ws(const snfft_shard* sh, const snfft_shard_ws* ws) {
+  if (!ws) throw InvalidArg("workspace is null");
+  if (!ws->local_a || !ws->local_b || !ws->status) throw InvalidArg("workspace has a null buffer");
+  if (sh->plan->host.n > sh->m + 1 && (!ws->shard_a || !ws->shard_b)) throw InvalidArg("workspace has a null buffer");
+  require_aligned16(ws->local_a, "ws->local_a");
+  require_aligned16(ws->local_b, "ws->local_b");
+}
+
+}  // namespace
+
 int snfft_shard_exchange(snfft_shard* sh, const void* const* peer_bufs, void* local_dev, int inverse,
                          void* stream) {
   return guarded([&] {
     if (!sh || !peer_bufs || !local_dev) throw InvalidArg("null argument");
     require_device(sh->plan);
-    if (sh->world > kMaxWorld) throw InvalidArg("peer-memory exchange supports at most 16 ranks");
-    const HostPlan& host = sh->plan->host;
-    const auto& shapes = host.levels[sh->m].shapes;
     DeviceGuard guard(sh->plan->device);
-    ShardPull X{};
-    X.rank = sh->rank;
-    X.world = sh->world;
-    X.mfact = host.fact[sh->m];
-    X.nblocks = host.fact[host.n] / host.fact[sh->m];
-    int64_t at = 0;
-    for (int r = 0; r < sh->world; ++r) {
-      if (!peer_bufs[r]) throw InvalidArg("null peer buffer");
-      X.peer[r] = static_cast<const double*>(peer_bufs[r]);
-      X.first[r] = shard_block_begin(X.nblocks, sh->world, r);
-      X.off[r] = (int32_t)at;
-      at += sh->size[r][sh->m];
+    shard_exchange_impl(sh, peer_bufs, local_dev, inverse != 0, (cudaStream_t)stream);
+  });
+}
+
+int snfft_shard_ws_sizes(const snfft_shard* sh, int64_t* sizes) {
+  return guarded([&] {
+    if (!sh || !sizes) throw InvalidArg("null argument");
+    const HostPlan& host = sh->plan->host;
+    const int n = host.n, m = sh->m;
+    const int64_t nblocks = host.fact[n] / host.fact[m];
+    int64_t cols = 0;
+    for (int r = 0; r < sh->world; ++r) cols = std::max(cols, nblocks * sh->size[r][m]);
+    int64_t b0 = 0, b1 = 0;
+    snfft_shard_blocks(sh, sh->rank, &b0, &b1);
+    int64_t work = 0;
+    for (int k = m + 1; k < n; ++k) work = std::max(work, (host.fact[n] / host.fact[k]) * sh->size[sh->rank][k]);
+    sizes[0] = cols;                      // column-shard buffer (same on every rank: symmetric allocation)
+    sizes[1] = (b1 - b0) * host.fact[m];  // local_a, local_b
+    sizes[2] = work;                      // shard_a, shard_b
+    sizes[3] = 2 * kMaxWorld;             // signal pad, in 8-byte words
+  });
+}
+
+int snfft_forward_sharded(snfft_shard* sh, const double* f_local_dev, double* fhat_compact_dev,
+                          const snfft_shard_ws* ws, void* stream_) {
+  return guarded([&] {
+    if (!sh || !f_local_dev || !fhat_compact_dev) throw InvalidArg("null argument");
+    require_device(sh->plan);
+    check_ws(sh, ws);
+    require_aligned16(f_local_dev, "f_local_dev");
+    DeviceGuard guard(sh->plan->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const HostPlan& host = sh->plan->host;
+    const int n = host.n, m = sh->m, q = sh->rank;
+    int64_t b0 = 0, b1 = 0;
+    snfft_shard_blocks(sh, q, &b0, &b1);
+    double* spectra = static_cast<double*>(ws->local_a);
+    // levels 2..m on this rank's blocks
+    forward_impl(sh->plan, m, f_local_dev, spectra, static_cast<double*>(ws->local_b), b1 - b0, false, stream);
+    shard_barrier(sh, ws, 0, stream);  // nobody still reads its column buffer
+    shard_exchange_impl(sh, ws->peer_cols, spectra, false, stream);  // push my blocks' columns to their owners
+    shard_barrier(sh, ws, 1, stream);  // every rank has pushed: my columns are complete
+    // levels m+1..n on my column shard
+    double* cur = static_cast<double*>(ws->peer_cols[q]);
+    for (int k = m + 1; k <= n; ++k) {
+      double* nxt = k == n ? fhat_compact_dev
+                           : static_cast<double*>((k - m) % 2 ? ws->shard_a : ws->shard_b);
+      shard_level_impl(sh, k, cur, nxt, false, stream);
+      cur = nxt;
     }
-    X.first[sh->world] = X.nblocks;
-    X.off[sh->world] = (int32_t)at;
-    if (at != X.mfact) throw std::runtime_error("column shards do not tile the S_m spectrum");
-    {
-      std::lock_guard<std::mutex> lock(sh->pull_mutex);
-      if (!sh->pull_idx) {
-        std::vector<int32_t> idx;
-        idx.reserve((size_t)X.mfact);
-        for (int r = 0; r < sh->world; ++r)
-          for (size_t i = 0; i < shapes.size(); ++i) {
-            const int64_t d = shapes[i].dim;
-            for (int64_t u = 0; u < d; ++u)
-              for (int c = 0; c < sh->w[r][sh->m][i]; ++c)
-                idx.push_back((int32_t)(shapes[i].off + u * d + sh->first[r][i] + c));
-          }
-        sh->pull_idx = shard_upload(sh, idx);
+  });
+}
+
+int snfft_inverse_sharded(snfft_shard* sh, const double* fhat_compact_dev, double* f_local_dev,
+                          const snfft_shard_ws* ws, void* stream_) {
+  return guarded([&] {
+    if (!sh || !f_local_dev || !fhat_compact_dev) throw InvalidArg("null argument");
+    require_device(sh->plan);
+    check_ws(sh, ws);
+    require_aligned16(f_local_dev, "f_local_dev");
+    DeviceGuard guard(sh->plan->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const HostPlan& host = sh->plan->host;
+    const int n = host.n, m = sh->m, q = sh->rank;
+    int64_t b0 = 0, b1 = 0;
+    snfft_shard_blocks(sh, q, &b0, &b1);
+    // levels n..m+1 backwards on my column shard; the last one writes my column buffer
+    double* cur = const_cast<double*>(fhat_compact_dev);  // only read
+    for (int k = n; k > m; --k) {
+      double* nxt;
+      if (k == m + 1) {
+        shard_barrier(sh, ws, 0, stream);  // nobody still pulls from my column buffer
+        nxt = static_cast<double*>(ws->peer_cols[q]);
+      } else {
+        nxt = static_cast<double*>((k - m) % 2 ? ws->shard_a : ws->shard_b);
       }
+      shard_level_impl(sh, k, nxt, cur, true, stream);
+      cur = nxt;
     }
-    X.idx = sh->pull_idx;
-    CUDA_OK(launch_shard_pull(X, static_cast<double*>(local_dev), inverse != 0, (cudaStream_t)stream));
+    shard_barrier(sh, ws, 1, stream);  // every rank's columns are complete
+    double* spectra = static_cast<double*>(ws->local_a);
+    shard_exchange_impl(sh, ws->peer_cols, spectra, true, stream);  // pull my blocks out of every rank's columns
+    inverse_impl(sh->plan, m, spectra, f_local_dev, static_cast<double*>(ws->local_b), b1 - b0, false, stream);
   });
 }
 
@@ -1141,6 +1449,79 @@ int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev,
     if (!src_dev || !idx_dev || !dst_dev) throw InvalidArg("null device buffer");
     if (count < 0 || width < 1) throw InvalidArg("bad gather shape");
     CUDA_OK(launch_gather(src_dev, idx_dev, dst_dev, count, width, (cudaStream_t)stream));
+  });
+}
+
+int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes, int32_t* panels,
+                       int64_t* bundles, int64_t* rows, int32_t* blocks, int32_t* stage_first) {
+  return guarded([&] {
+    if (!plan || !sizes) throw InvalidArg("null argument");
+    if (k < kPhaseMinLevel || k > plan->host.n) throw InvalidArg("row-group phases exist for levels 9..n");
+    const LevelProgram& prog = plan->host.programs[k];
+    const int nphases = (int)prog.panels[0].phases.size();
+    if (phase < 1 || phase >= nphases) throw InvalidArg("phase must be in 1..phases-1 (phase 0 = generated stages 1..4)");
+    // the same builder as the device tables, "uploading" into host memory
+    std::vector<std::vector<char>> keep;
+    auto up = [&](const auto& v) {
+      using T = typename std::decay<decltype(v)>::type::value_type;
+      keep.emplace_back((const char*)v.data(), (const char*)(v.data() + v.size()));
+      return (T*)keep.back().data();
+    };
+    std::vector<PhaseHost> devs;
+    const LevelLayout lay = plain_layout(plan, k);
+    build_phase_devs(prog, lay, prog.coef.data(), up, devs);
+    const BundleDev& D = devs[phase].dev;
+    int32_t nbundles = 0;
+    for (int p = 0; p < D.npanels; ++p) nbundles += D.panels[p].nbundles;
+    int64_t nrows = 0, nblocks = 0;
+    for (int b = 0; b < nbundles; ++b) {
+      nrows += D.bundles[b].nrows & 0xffffu;
+      nblocks += D.stage_first[D.bundles[b].stage_off + D.nstages * (kPhaseWarpsHost + 1) - 1];
+    }
+    sizes[0] = D.npanels;
+    sizes[1] = nbundles;
+    sizes[2] = (int32_t)nrows;
+    sizes[3] = (int32_t)nblocks;
+    sizes[4] = nbundles * D.nstages * (kPhaseWarpsHost + 1);
+    sizes[5] = D.cols_per_lane;
+    sizes[6] = D.nstages;
+    sizes[7] = D.max_rows;
+    sizes[8] = prog.panels[0].phases[phase].stage_lo;
+    sizes[9] = nphases;
+    for (int p = 0; p < D.npanels && panels; ++p) {
+      const BundlePanelDev& pd = D.panels[p];
+      const int32_t rec[5] = {pd.d, pd.tiles, pd.bundle_off, pd.nbundles, pd.pack};
+      std::copy(rec, rec + 5, panels + 5 * p);
+    }
+    for (int b = 0; b < nbundles && bundles; ++b) {
+      const Bundle& B = D.bundles[b];
+      bundles[4 * b] = B.row_off;
+      bundles[4 * b + 1] = B.blk_off;
+      bundles[4 * b + 2] = B.stage_off;
+      bundles[4 * b + 3] = B.nrows & 0xffffu;
+      for (uint32_t r = 0; r < (B.nrows & 0xffffu) && rows; ++r) {
+        rows[3 * (B.row_off + r)] = D.row_xoff[B.row_off + r];
+        rows[3 * (B.row_off + r) + 1] = D.row_dest[B.row_off + r];
+        rows[3 * (B.row_off + r) + 2] = r >= (B.nrows >> 16) ? 1 : 0;
+      }
+    }
+    for (int64_t b = 0; b < nblocks && blocks; ++b) {
+      for (int a = 0; a < kMaxBlock; ++a) blocks[8 * b + a] = a < D.blocks_f[b].m ? D.blocks_f[b].loc[a] : -1;
+      blocks[8 * b + 5] = D.blocks_f[b].m;
+      blocks[8 * b + 6] = (int32_t)D.blocks_f[b].coef;
+      blocks[8 * b + 7] = (int32_t)D.blocks_i[b].coef;
+    }
+    for (int i = 0; i < sizes[4] && stage_first; ++i) stage_first[i] = (int32_t)D.stage_first[i];
+  });
+}
+
+int snfft_export_coef(const snfft_plan* plan, int k, double* coef, int64_t* count) {
+  return guarded([&] {
+    if (!plan || !count) throw InvalidArg("null argument");
+    if (k < 2 || k > plan->host.n) throw InvalidArg("level k must be in 2..n");
+    const std::vector<double>& pool = plan->host.programs[k].coef;
+    *count = (int64_t)pool.size();
+    if (coef) std::copy(pool.begin(), pool.end(), coef);
   });
 }
 

@@ -42,28 +42,47 @@ struct Tile {
   int32_t cap;
 };
 
-// Row-group phase of a level (levels >= 9): see plan.hpp
-struct PhasePanelDev {
-  int32_t d;         // columns of the panel
-  int32_t tiles;     // ceil(d / (32 * cols_per_lane))
-  int32_t grp_off;   // first group in PhaseDev::groups
-  int32_t ngroups;
-  int64_t item_off;  // prefix sum of ngroups * tiles
-  int32_t pack;      // narrow panels (d <= 16): floor(32 / d) members of the lg loop share a warp
-  int32_t reserved;
+// Row-group phase of a level (levels >= 9): see plan.hpp.  The groups of a panel are packed into
+// "bundles" (as many whole groups as fit the shared-memory tile of a CTA); a CTA loads the rows of
+// one bundle for a tile of 32 * cols_per_lane columns, runs the bundle's blocks stage by stage
+// (one barrier per stage, warps take blocks round-robin, lanes = columns) and stores the rows.
+struct alignas(16) BundleBlock {
+  uint16_t loc[kMaxBlock];  // rows of the block, as indices into the bundle's row list
+  uint8_t m;
+  uint8_t pad;
+  uint32_t coef;            // offset (doubles) of the m x m matrix in the level's coefficient pool
 };
-
-struct PhaseDev {
-  const PhasePanelDev* panels;
-  const PhaseGroup* groups;  // row_off / blk_off are absolute here
-  const PhaseRow* rows;
-  const PhaseBlock* blocks;
+static_assert(sizeof(BundleBlock) == 16, "BundleBlock must be 16 bytes");
+struct Bundle {
+  uint32_t row_off;    // first row in BundleDev::row_xoff / row_dest
+  uint32_t blk_off;    // first block in BundleDev::blocks_*
+  uint32_t stage_off;  // stage_first[stage_off + s * 17 + w] .. [+ w + 1]: blocks of warp w in the s-th stage (relative)
+  uint32_t nrows;      // low 16 bits: rows; high 16 bits: rows that are NOT finished in this phase (they come first)
+};
+struct BundlePanelDev {
+  int32_t d;           // columns of the panel
+  int32_t tiles;       // ceil(d / (32 * cols_per_lane)); 1 when several lg members share the tile
+  int32_t bundle_off;  // first bundle in BundleDev::bundles
+  int32_t nbundles;
+  int64_t item_off;    // prefix sum of nbundles * tiles
+  int32_t pack;        // narrow panels: floor(32 * cols_per_lane / d) members of the lg loop side by side
+  int32_t magic;       // ceil(65536 / d): (c * magic) >> 16 = c / d for c < 256
+};
+struct BundleDev {
+  const BundlePanelDev* panels;
+  const Bundle* bundles;
+  const uint32_t* row_xoff;     // per row: offset of its in-place slot in the x-side buffer
+  const uint32_t* row_dest;     // per row: offset of the finished row in the spectrum-side buffer
+  const BundleBlock* blocks_f;  // forward coefficients
+  const BundleBlock* blocks_i;  // inverse coefficients (same rows)
+  const uint32_t* stage_first;
   const double* coef;
   int64_t nitems;
   int64_t in_stride, out_stride;  // group strides of the X-side and spectrum-side buffers
   int32_t npanels;
-  int32_t max_rows;
-  int32_t cols_per_lane;  // 1, 2 or 4: a warp covers 32 * cols_per_lane columns (PhasePanelDev::tiles)
+  int32_t max_rows;       // rows of the largest bundle (shared-memory tile = max_rows x 32 * cols_per_lane)
+  int32_t cols_per_lane;  // 1, 2, 4 or 8
+  int32_t nstages;
 };
 
 // In-place phase 1 of a large level as generated register programs: one entry per (panel, upper
@@ -109,6 +128,15 @@ struct ShardPull {
   const int32_t* idx;             // device, m! entries
   int64_t nblocks, mfact;
   int32_t rank, world;
+};
+
+// Device-side barrier between ranks (kernels.cu: shard_barrier_kernel).  pads[r] = rank r's signal
+// pad in peer-accessible memory: unsigned long long [channels][kMaxWorld].
+struct ShardBarrier {
+  unsigned long long* pads[kMaxWorld];
+  unsigned long long epoch;
+  int* status;  // device word of the calling rank, set to 1 on a timeout
+  int32_t rank, world, channel;
 };
 
 }  // namespace snfft

@@ -25,15 +25,15 @@
 
 namespace snfft {
 
-int64_t g_launch_count = 0;
-bool g_force_table_driven = false;
+std::atomic<int64_t> g_launch_count{0};
+std::atomic<bool> g_force_table_driven{false};
 
 namespace {
 struct TimedLaunch {
   int kind;
   cudaEvent_t start, stop;
 };
-bool g_timing = false;
+std::atomic<bool> g_timing{false};
 std::vector<TimedLaunch> g_timed;
 std::vector<cudaEvent_t> g_event_pool;
 std::mutex g_timing_mu;
@@ -54,8 +54,8 @@ struct LaunchScope {
   cudaStream_t stream;
   bool on;
   TimedLaunch t;
-  LaunchScope(int kind, cudaStream_t s) : stream(s), on(g_timing) {
-    ++g_launch_count;
+  LaunchScope(int kind, cudaStream_t s) : stream(s), on(g_timing.load(std::memory_order_relaxed)) {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     if (on) {
       std::lock_guard<std::mutex> lock(g_timing_mu);
       t.kind = kind;
@@ -710,23 +710,54 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// row-group phase kernel (levels >= 9).  One warp = one (row group, 32-column tile): the lanes own
-// one column each, the group's rows sit in a lane-private shared-memory column, the group's blocks
-// run back to back (uniform control flow, no barriers), rows go back with coalesced 256-byte runs.
+// row-group phase kernel (levels >= 9).  One CTA = one (bundle of row groups, tile of 32 * CPL
+// columns): the rows of the bundle are staged into shared memory with cp.async (coalesced runs of
+// 256 bytes per warp and row), the bundle's blocks run stage by stage (warps take blocks
+// round-robin, lanes = columns, CPL columns per lane share one read of the block descriptor and of
+// its coefficients; one barrier per stage), and the rows go back in place or, when finished, to the
+// spectrum.  Narrow panels (column shards) put several members of the group loop side by side.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPhaseWarps = 8;
+// One persistent CTA of 16 warps per SM with TWO tiles in shared memory: the rows of the next unit
+// of work are in flight (cp.async) while the current tile runs its stages and is stored.  The
+// instruction budget is what bounds this kernel (the DFMAs are < 0.3 warp instructions per element),
+// so everything per block is shared by as many columns as shared memory allows (CPL up to 8: 256
+// columns per descriptor read), rows are addressed with 32-bit offsets off one 64-bit base, and the
+// rows of a bundle are sorted so that neither the load nor the store loop selects a buffer per row.
+constexpr int kPhaseWarps = 16;
+constexpr int kPhaseMaxPanels = 64;  // >= number of partitions of 11 (56)
+struct PhaseLaunch {
+  uint32_t work_off[kPhaseMaxPanels + 1];  // prefix sums of bundles * tiles * ceil(lgroups / pack) over the panels
+};
 
-// y[c][a] = sum_b cm[a][b] x[c][b] for CPL columns with one load of the coefficients
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async8_s(unsigned smem_addr, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+
+// y[c][a] = sum_b cm[a][b] x[c][b] for CPL columns per lane with one read of the descriptor and of
+// the m x m matrix (16-byte loads; every matrix starts on a 16-byte boundary, the pool is padded)
 template <int M, int CPL>
-__device__ __forceinline__ void block_apply(const double* __restrict__ cmat, const uint8_t* loc, double* col) {
-  double cm[M * M];
+__device__ __forceinline__ void block_apply(const double* __restrict__ cmat, const BundleBlock& blk,
+                                            double* __restrict__ col) {
+  constexpr int W = 32 * CPL;
+  double cm[M * M + 1];
+  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cmat);
 #pragma unroll
-  for (int i = 0; i < M * M; ++i) cm[i] = __ldg(cmat + i);
+  for (int i = 0; i < (M * M + 1) / 2; ++i) {
+    const double2 v = __ldg(c2 + i);
+    cm[2 * i] = v.x;
+    if (2 * i + 1 < M * M + 1) cm[2 * i + 1] = v.y;
+  }
+  double* row[M];
+#pragma unroll
+  for (int b = 0; b < M; ++b) row[b] = col + (int)blk.loc[b] * W;
 #pragma unroll
   for (int cc = 0; cc < CPL; ++cc) {
     double x[M], y[M];
 #pragma unroll
-    for (int b = 0; b < M; ++b) x[b] = col[loc[b] * (32 * CPL) + cc * 32];
+    for (int b = 0; b < M; ++b) x[b] = row[b][cc * 32];
 #pragma unroll
     for (int a = 0; a < M; ++a) {
       double acc = cm[a * M] * x[0];
@@ -735,66 +766,172 @@ __device__ __forceinline__ void block_apply(const double* __restrict__ cmat, con
       y[a] = acc;
     }
 #pragma unroll
-    for (int a = 0; a < M; ++a) col[loc[a] * (32 * CPL) + cc * 32] = y[a];
+    for (int a = 0; a < M; ++a) row[a][cc * 32] = y[a];
   }
 }
 
-// CPL = columns per lane: a warp covers 32 * CPL columns of one row group (tile = [rows][32 * CPL])
+// a unit of work: one bundle, one tile of columns (or `pack` members of the group loop side by side)
+struct PhaseWork {
+  const uint32_t* xoff;   // per row: offset in the x-side buffer
+  const uint32_t* dest;   // per row >= nlow: offset in the spectrum-side buffer (indexed like xoff)
+  const BundleBlock* blocks;
+  const uint32_t* split;
+  int nrows, nlow;        // rows [0, nlow) stay on the x side, rows [nlow, nrows) are finished in this phase
+  int d, pack, tile, magic;
+  uint32_t lg0;
+};
+
+// CPL = columns per lane: a tile is [rows of the bundle][32 * CPL columns]
 template <bool INV, int CPL>
-__global__ void __launch_bounds__(kPhaseWarps * 32)
-phase_kernel(PhaseDev P, double* __restrict__ xside, double* __restrict__ sside, int64_t lgroups) {
+__global__ void __launch_bounds__(kPhaseWarps * 32, 1)
+phase_kernel(BundleDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __restrict__ sside,
+             uint32_t lgroups) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int W = 32 * CPL;
-  double* col = sm + (size_t)warp * P.max_rows * W + lane;
-  for (int64_t item = (int64_t)blockIdx.x * kPhaseWarps + warp; item < P.nitems;
-       item += (int64_t)gridDim.x * kPhaseWarps) {
-    int pi = 0;
-    while (pi + 1 < P.npanels && item >= P.panels[pi + 1].item_off) ++pi;
-    const PhasePanelDev pan = P.panels[pi];
-    const int64_t rem = item - pan.item_off;
-    const int group = (int)(rem / pan.tiles), tile = (int)(rem - (int64_t)group * pan.tiles);
-    // lane -> (member of the lg loop, column): one member per warp, or `pack` members side by side
-    // when the panel is at most 16 columns wide (column shards)
-    const int sub = pan.pack > 1 ? lane / pan.d : 0;
-    const int c0 = pan.pack > 1 ? lane - sub * pan.d : tile * W + lane;
-    const PhaseGroup G = P.groups[pan.grp_off + group];
-    const PhaseRow* __restrict__ rows = P.rows + G.row_off;
-    const PhaseBlock* __restrict__ blocks = P.blocks + G.blk_off;
-    for (int64_t lg0 = blockIdx.y; lg0 * pan.pack < lgroups; lg0 += gridDim.y) {
-      const int64_t lg = lg0 * pan.pack + sub;
-      const bool member = sub < pan.pack && lg < lgroups;
-      double* xs = xside + lg * P.in_stride + c0;
-      double* ss = sside + lg * P.out_stride + c0;
-      // all rows of the group in flight at once: global -> lane-private shared column, no registers
-#pragma unroll 8
-      for (int r = 0; r < G.nrows; ++r) {
-        const PhaseRow row = rows[r];
-        const double* src = (INV && row.final) ? ss + row.dest : xs + row.xoff;
+  const BundleBlock* __restrict__ all_blocks = INV ? P.blocks_i : P.blocks_f;
+  const uint32_t nwork = Lp.work_off[P.npanels];
+
+  auto decode = [&](uint32_t w, PhaseWork& k) {
+    int lo = 0, hi = P.npanels - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (Lp.work_off[mid] <= w) lo = mid; else hi = mid - 1;
+    }
+    const BundlePanelDev pan = P.panels[lo];
+    const uint32_t nlg = (lgroups + pan.pack - 1) / pan.pack;
+    const uint32_t rem = w - Lp.work_off[lo];
+    const uint32_t item = rem / nlg;  // the lg loop is the fastest index: CTAs that run together share tables
+    k.lg0 = rem - item * nlg;
+    const uint32_t bundle = item / (uint32_t)pan.tiles;
+    k.tile = (int)(item - bundle * (uint32_t)pan.tiles);
+    const Bundle B = P.bundles[pan.bundle_off + bundle];
+    k.xoff = P.row_xoff + B.row_off;
+    k.dest = P.row_dest + B.row_off;
+    k.blocks = all_blocks + B.blk_off;
+    k.split = P.stage_first + B.stage_off;
+    k.nrows = (int)(B.nrows & 0xffffu);
+    k.nlow = (int)(B.nrows >> 16);
+    k.d = pan.d;
+    k.pack = pan.pack;
+    k.magic = pan.magic;
+  };
+  // lane -> CPL (member of the lg loop, column) pairs of a unit of work, as 32-bit element offsets
+  // relative to the buffers advanced to the first member; 0xffffffff = no column
+  auto columns = [&](const PhaseWork& k, uint32_t (&xo)[CPL], uint32_t (&so)[CPL]) {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc)
-          if (member && c0 + cc * 32 < pan.d) cp_async8(&col[r * W + cc * 32], src + cc * 32);
-      }
-      cp_async_wait_all();  // a lane only reads what it copied itself
-      for (int bi = 0; bi < G.nblk; ++bi) {
-        const PhaseBlock b = blocks[INV ? G.nblk - 1 - bi : bi];
-        const double* cmat = P.coef + (INV ? b.coef_i : b.coef_f);
-        switch (b.m) {
-          case 2: block_apply<2, CPL>(cmat, b.loc, col); break;
-          case 3: block_apply<3, CPL>(cmat, b.loc, col); break;
-          case 4: block_apply<4, CPL>(cmat, b.loc, col); break;
-          default: block_apply<5, CPL>(cmat, b.loc, col); break;
-        }
-      }
-#pragma unroll 8
-      for (int r = 0; r < G.nrows; ++r) {
-        const PhaseRow row = rows[r];
-        double* dst = (!INV && row.final) ? ss + row.dest : xs + row.xoff;
-#pragma unroll
-        for (int cc = 0; cc < CPL; ++cc)
-          if (member && c0 + cc * 32 < pan.d) dst[cc * 32] = col[r * W + cc * 32];
+    for (int cc = 0; cc < CPL; ++cc) {
+      const int c = lane + 32 * cc;
+      if (k.pack > 1) {
+        const int sub = (c * k.magic) >> 16;  // c / d for c < 256 (magic = ceil(65536 / d))
+        const int cg = c - sub * k.d;
+        const bool ok = sub < k.pack && k.lg0 * (uint32_t)k.pack + sub < lgroups;
+        xo[cc] = ok ? (uint32_t)sub * (uint32_t)P.in_stride + cg : 0xffffffffu;
+        so[cc] = ok ? (uint32_t)sub * (uint32_t)P.out_stride + cg : 0xffffffffu;
+      } else {
+        const int cg = k.tile * W + c;
+        xo[cc] = so[cc] = cg < k.d ? (uint32_t)cg : 0xffffffffu;
       }
     }
+  };
+  // all rows of the bundle in flight at once: global -> shared tile, no registers
+  auto issue_loads = [&](const PhaseWork& k, double* tile) {
+    uint32_t xo[CPL], so[CPL];
+    columns(k, xo, so);
+    const int64_t first = (int64_t)k.lg0 * k.pack;
+    const double* xb = xside + first * P.in_stride;
+    const double* sb = sside + first * P.out_stride;
+    const unsigned t0 = (unsigned)__cvta_generic_to_shared(tile + lane);
+    const int nx = INV ? k.nlow : k.nrows;  // rows read from the x side
+#pragma unroll 2
+    for (int r = warp; r < nx; r += kPhaseWarps) {
+      const uint32_t off = __ldg(k.xoff + r);
+#pragma unroll
+      for (int cc = 0; cc < CPL; ++cc)
+        if (xo[cc] != 0xffffffffu) cp_async8_s(t0 + (unsigned)(r * W + cc * 32) * 8u, xb + (off + xo[cc]));
+    }
+    if (INV) {
+      const int rs = k.nlow + ((warp - k.nlow) & (kPhaseWarps - 1));  // keep the round-robin over warps
+#pragma unroll 2
+      for (int r = rs; r < k.nrows; r += kPhaseWarps) {
+        const uint32_t off = __ldg(k.dest + r);
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc)
+          if (so[cc] != 0xffffffffu) cp_async8_s(t0 + (unsigned)(r * W + cc * 32) * 8u, sb + (off + so[cc]));
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int tile_elems = P.max_rows * W;
+  PhaseWork cur, nxt;
+  uint32_t w = blockIdx.x;
+  if (w >= nwork) return;
+  decode(w, cur);
+  issue_loads(cur, sm);
+  int buf = 0;
+  while (true) {
+    const uint32_t wn = w + gridDim.x;
+    const bool more = wn < nwork;
+    if (more) {
+      decode(wn, nxt);
+      issue_loads(nxt, sm + (buf ^ 1) * tile_elems);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    double* col = sm + buf * tile_elems + lane;
+    for (int st = 0; st < P.nstages; ++st) {
+      const int s = INV ? P.nstages - 1 - st : st;
+      const int b0 = (int)cur.split[s * (kPhaseWarps + 1) + warp], b1 = (int)cur.split[s * (kPhaseWarps + 1) + warp + 1];
+      // the next descriptor is fetched while the current block runs
+      BundleBlock cb{};
+      if (b0 < b1) cb = cur.blocks[b0];
+      for (int bi = b0; bi < b1; ++bi) {
+        BundleBlock nb{};
+        if (bi + 1 < b1) nb = cur.blocks[bi + 1];
+        const double* cmat = P.coef + cb.coef;
+        switch (cb.m) {
+          case 2: block_apply<2, CPL>(cmat, cb, col); break;
+          case 3: block_apply<3, CPL>(cmat, cb, col); break;
+          case 4: block_apply<4, CPL>(cmat, cb, col); break;
+          default: block_apply<5, CPL>(cmat, cb, col); break;
+        }
+        cb = nb;
+      }
+      __syncthreads();
+    }
+    {
+      uint32_t xo[CPL], so[CPL];
+      columns(cur, xo, so);
+      const int64_t first = (int64_t)cur.lg0 * cur.pack;
+      double* xb = xside + first * P.in_stride;
+      double* sb = sside + first * P.out_stride;
+      const int nx = INV ? cur.nrows : cur.nlow;  // rows written to the x side
+#pragma unroll 2
+      for (int r = warp; r < nx; r += kPhaseWarps) {
+        const uint32_t off = __ldg(cur.xoff + r);
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc)
+          if (xo[cc] != 0xffffffffu) xb[off + xo[cc]] = col[r * W + cc * 32];
+      }
+      if (!INV) {
+        const int rs = cur.nlow + ((warp - cur.nlow) & (kPhaseWarps - 1));
+#pragma unroll 2
+        for (int r = rs; r < cur.nrows; r += kPhaseWarps) {
+          const uint32_t off = __ldg(cur.dest + r);
+#pragma unroll
+          for (int cc = 0; cc < CPL; ++cc)
+            if (so[cc] != 0xffffffffu) sb[off + so[cc]] = col[r * W + cc * 32];
+        }
+      }
+    }
+    if (!more) break;
+    __syncthreads();  // this tile is free for the loads of the work after next
+    cur = nxt;
+    w = wn;
+    buf ^= 1;
   }
 }
 
@@ -1197,6 +1334,31 @@ shard_exchange_kernel(ShardPull X, double* __restrict__ local) {
   }
 }
 
+// Barrier between the ranks of a sharded transform, on the device: every rank raises its flag in
+// every peer's signal pad (release, system scope) and waits until all peers have raised theirs in
+// its own pad (acquire).  Flags are epochs that only grow, so the pads are never reset.  A peer that
+// never arrives makes the kernel give up after ~2 s and set the status word instead of hanging.
+__global__ void shard_barrier_kernel(ShardBarrier Bq) {
+  const int t = threadIdx.x;
+  if (t >= Bq.world) return;
+  __threadfence_system();
+  unsigned long long* theirs = Bq.pads[t] + (size_t)Bq.channel * kMaxWorld + Bq.rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(Bq.epoch) : "memory");
+  const unsigned long long* mine = Bq.pads[Bq.rank] + (size_t)Bq.channel * kMaxWorld + t;
+  const long long t0 = clock64();
+  while (true) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= Bq.epoch) break;
+    if (clock64() - t0 > 4000000000LL) {
+      *Bq.status = 1;  // a peer did not arrive
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
 Facts make_facts() {
   Facts F;
   F.f[0] = 1;
@@ -1223,6 +1385,8 @@ cudaError_t prepare_kernels() {
   if ((e = allow_big_smem(phase_kernel<true, 2>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 4>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<true, 4>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false, 8>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true, 8>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
@@ -1260,7 +1424,7 @@ cudaError_t launch_level8(const double* in, double* out, int64_t groups, bool in
   launch.first_cta[gen::kL8NumPanels] = (int)total;  // CTAs per super-chunk
   total *= (groups + kL8Super - 1) / kL8Super;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+  LaunchScope scope(inverse ? kKindLevel8Inv : kKindLevel8Fwd, stream);
   const size_t smem = kL8SmemDoubles * sizeof(double);
   if (inverse)
     level8_kernel<true><<<(unsigned)total, kL8Threads, smem, stream>>>(launch, in, out, groups);
@@ -1271,17 +1435,17 @@ cudaError_t launch_level8(const double* in, double* out, int64_t groups, bool in
 }  // namespace
 
 cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, size_t smem_bytes,
-                         const double* in, double* out, int64_t groups, bool inverse, int num_sms,
-                         cudaStream_t stream) {
+                         const double* in, double* out, int64_t groups, bool inverse, bool table_driven,
+                         int num_sms, cudaStream_t stream) {
   if (groups <= 0 || ntiles <= 0) return cudaSuccess;
-  if (L.k == 8 && !g_force_table_driven) return launch_level8(in, out, groups, inverse, stream);
+  if (L.k == 8 && !table_driven) return launch_level8(in, out, groups, inverse, stream);
   // enough CTAs to fill the machine a few times over; each CTA strides over group chunks
   int64_t y = (8LL * num_sms + ntiles - 1) / ntiles;
   if (y > groups) y = groups;
   if (y < 1) y = 1;
   if (y > 65535) y = 65535;
   dim3 grid((unsigned)ntiles, (unsigned)y);
-  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+  LaunchScope scope(kKindLevelTable, stream);
   if (inverse)
     level_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(L, tiles_dev, in, out, groups);
   else
@@ -1305,30 +1469,37 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
 }
 
 template <int CPL>
-static cudaError_t launch_phase_cpl(const PhaseDev& P, double* xside, double* sside, int64_t lgroups,
-                                    bool inverse, int num_sms, cudaStream_t stream) {
-  const size_t smem = (size_t)kPhaseWarps * P.max_rows * 32 * CPL * sizeof(double);
-  int64_t gy = lgroups < 64 ? lgroups : 64;
-  int64_t gx = (P.nitems + kPhaseWarps - 1) / kPhaseWarps;
-  const int64_t want = 16LL * num_sms;  // enough CTAs to fill the machine; the rest is grid-stride
-  if (gx * gy > want) gx = (want + gy - 1) / gy;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+static cudaError_t launch_phase_cpl(const BundleDev& P, const PhaseLaunch& Lp, double* xside, double* sside,
+                                    int64_t lgroups, bool inverse, int num_sms, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)P.max_rows * 32 * CPL * sizeof(double);
+  int64_t grid = Lp.work_off[P.npanels];
+  if (grid > num_sms) grid = num_sms;  // persistent: one CTA per SM, units of work grid-strided
+  LaunchScope scope(inverse ? kKindPhaseInv : kKindPhaseFwd, stream);
   if (inverse)
-    phase_kernel<true, CPL><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+    phase_kernel<true, CPL><<<(unsigned)grid, kPhaseWarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups);
   else
-    phase_kernel<false, CPL><<<grid, kPhaseWarps * 32, smem, stream>>>(P, xside, sside, lgroups);
+    phase_kernel<false, CPL><<<(unsigned)grid, kPhaseWarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups);
   return cudaGetLastError();
 }
 
-cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
-                         int num_sms, cudaStream_t stream) {
+cudaError_t launch_phase(const BundleDev& P, const int32_t* panel_items, const int32_t* panel_pack,
+                         double* xside, double* sside, int64_t lgroups, bool inverse, int num_sms,
+                         cudaStream_t stream) {
   if (lgroups <= 0 || P.nitems <= 0) return cudaSuccess;
+  if (P.npanels > kPhaseMaxPanels || lgroups > 0x7fffffffLL) return cudaErrorInvalidValue;
+  PhaseLaunch Lp;
+  int64_t at = 0;
+  for (int p = 0; p < P.npanels; ++p) {
+    Lp.work_off[p] = (uint32_t)at;
+    at += (int64_t)panel_items[p] * ((lgroups + panel_pack[p] - 1) / panel_pack[p]);
+    if (at > 0x7fffffffLL) return cudaErrorInvalidValue;
+  }
+  for (int p = P.npanels; p <= kPhaseMaxPanels; ++p) Lp.work_off[p] = (uint32_t)at;
   switch (P.cols_per_lane) {
-    case 4: return launch_phase_cpl<4>(P, xside, sside, lgroups, inverse, num_sms, stream);
-    case 2: return launch_phase_cpl<2>(P, xside, sside, lgroups, inverse, num_sms, stream);
-    default: return launch_phase_cpl<1>(P, xside, sside, lgroups, inverse, num_sms, stream);
+    case 8: return launch_phase_cpl<8>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
+    case 4: return launch_phase_cpl<4>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
+    case 2: return launch_phase_cpl<2>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
+    default: return launch_phase_cpl<1>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
   }
 }
 
@@ -1348,14 +1519,14 @@ cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int6
     const bool rows_pass = inverse ? step == 0 : step == 1;
     if (rows_pass) {
       if (P.nrow_items <= 0) continue;
-      LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+      LaunchScope scope(kKindP0, stream);
       if (inverse)
         p0_rows_kernel<true><<<grid_for(P.nrow_items), 256, 0, stream>>>(P, xside, sside, lgroups);
       else
         p0_rows_kernel<false><<<grid_for(P.nrow_items), 256, 0, stream>>>(P, xside, sside, lgroups);
     } else {
       if (P.nitems <= 0) continue;
-      LaunchScope scope(inverse ? kKindLevelInv : kKindLevelFwd, stream);
+      LaunchScope scope(kKindP1, stream);
       if (inverse)
         p1_inplace_kernel<true><<<grid_for(P.nitems), 256, 0, stream>>>(P, xside, lgroups);
       else
@@ -1448,11 +1619,17 @@ cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, c
   if (gx > 256) gx = 256;
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  LaunchScope scope(kKindOther, stream);
+  LaunchScope scope(kKindExchange, stream);
   if (inverse)
     shard_exchange_kernel<true><<<grid, 256, 0, stream>>>(X, local);
   else
     shard_exchange_kernel<false><<<grid, 256, 0, stream>>>(X, local);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shard_barrier(const ShardBarrier& Bq, cudaStream_t stream) {
+  LaunchScope scope(kKindExchange, stream);
+  shard_barrier_kernel<<<1, 32, 0, stream>>>(Bq);
   return cudaGetLastError();
 }
 

@@ -3,29 +3,36 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "device_plan.hpp"
 
 namespace snfft {
 
-extern int64_t g_launch_count;
-extern bool g_force_table_driven;  // tests: route level 8 through the table-driven kernel too
+extern std::atomic<int64_t> g_launch_count;
+extern std::atomic<bool> g_force_table_driven;  // tests: route level 8 through the table-driven kernel too
 
 // Optional per-launch timing (bench.py): when enabled every launch is bracketed by CUDA events on
 // its own stream; timing_read() synchronises the recorded events and returns the totals per kind.
-enum KernelKind { kKindFusedFwd = 0, kKindFusedInv, kKindLevelFwd, kKindLevelInv, kKindReorder,
+enum KernelKind { kKindFusedFwd = 0, kKindFusedInv, kKindLevel8Fwd, kKindLevel8Inv, kKindLevelTable,
+                  kKindP1, kKindP0, kKindPhaseFwd, kKindPhaseInv, kKindExchange, kKindReorder,
                   kKindYor, kKindDgemm, kKindOther, kNumKinds };
 void timing_enable(bool on);
 void timing_read(double* ms_by_kind, int64_t* launches_by_kind);  // also resets the totals
 
-// Streaming level kernel: global -> shared tile -> stages -> global.
+// Streaming level kernel: global -> shared tile -> stages -> global.  table_driven = false lets
+// level 8 of a whole transform run as generated register programs (they assume the full 8! pitch,
+// so column shards always pass true).
 cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, size_t smem_bytes,
-                         const double* in, double* out, int64_t groups, bool inverse, int num_sms,
-                         cudaStream_t stream);
+                         const double* in, double* out, int64_t groups, bool inverse, bool table_driven,
+                         int num_sms, cudaStream_t stream);
 
 // One row-group phase of a level: xside holds the in-place rows (input of the level, clobbered by
 // the forward direction; output of the level in the inverse direction), sside the finished rows.
-cudaError_t launch_phase(const PhaseDev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
-                         int num_sms, cudaStream_t stream);
+// panel_items[p] = bundles * tiles of panel p, panel_pack[p] = its pack (host copies of the device tables).
+cudaError_t launch_phase(const BundleDev& P, const int32_t* panel_items, const int32_t* panel_pack,
+                         double* xside, double* sside, int64_t lgroups, bool inverse, int num_sms,
+                         cudaStream_t stream);
 
 // Stages 1..4 of a large level as in-place generated programs plus the pass that moves the rows
 // finished after stage 4 to / from the spectrum-side buffer.
@@ -56,6 +63,9 @@ cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, in
 
 // the exchange of the sharded transform as P2P loads from peer memory (see ShardPull)
 cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, cudaStream_t stream);
+
+// device-side barrier between the ranks of a sharded transform (see ShardBarrier)
+cudaError_t launch_shard_barrier(const ShardBarrier& B, cudaStream_t stream);
 
 cudaError_t prepare_kernels();  // opt in to large dynamic shared memory (once per process)
 

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <unordered_map>
@@ -324,16 +325,7 @@ void build_panel(const HostPlan& plan, int k, int mu, LevelProgram& level,
 // Cut the stages of a panel into phases and its rows into groups closed under each phase.
 void build_phases(PanelProgram& P) {
   const int k = P.k, d = P.d, rows = k * d;
-  // stage ranges: [1..4] then chunks of up to 4 stages, the last two chunks balanced
-  std::vector<std::pair<int, int>> ranges;
-  ranges.push_back({1, std::min(4, k - 1)});
-  int lo = 5;
-  while (lo <= k - 1) {
-    const int left = k - lo;  // stages lo..k-1
-    int len = left <= 4 ? left : (left <= 6 ? (left + 1) / 2 : 4);
-    ranges.push_back({lo, lo + len - 1});
-    lo += len;
-  }
+  const std::vector<std::pair<int, int>> ranges = phase_ranges(k);
   std::vector<int> last_writer(rows, -1);
   for (size_t b = 0; b < P.blocks.size(); ++b)
     for (int a = 0; a < P.blocks[b].m; ++a) last_writer[P.blocks[b].slot[a]] = (int)b;
@@ -382,8 +374,8 @@ void build_phases(PanelProgram& P) {
       PhaseGroup G;
       G.row_off = (uint32_t)ph.rows.size();
       G.blk_off = (uint32_t)ph.blocks.size();
-      G.nrows = (uint16_t)grows[g].size();
-      G.nblk = (uint16_t)gblocks[g].size();
+      G.nrows = (uint32_t)grows[g].size();
+      G.nblk = (uint32_t)gblocks[g].size();
       ph.max_rows = std::max<int>(ph.max_rows, G.nrows);
       for (size_t q = 0; q < grows[g].size(); ++q) {
         const int s = grows[g][q];
@@ -396,7 +388,8 @@ void build_phases(PanelProgram& P) {
         const Block& blk = P.blocks[b];
         PhaseBlock pb{};
         pb.m = blk.m;
-        for (int a = 0; a < blk.m; ++a) pb.loc[a] = (uint8_t)local[blk.slot[a]];
+        pb.stage = (uint8_t)(b / d + 1);
+        for (int a = 0; a < blk.m; ++a) pb.loc[a] = (uint16_t)local[blk.slot[a]];
         pb.coef_f = blk.coef_f;
         pb.coef_i = blk.coef_i;
         ph.blocks.push_back(pb);
@@ -408,6 +401,46 @@ void build_phases(PanelProgram& P) {
 }
 
 }  // namespace
+
+std::vector<std::pair<int, int>> phase_ranges(int k) {
+  std::vector<int> ends;
+  if (const char* env = std::getenv("SNFFT_WINDOWS")) {
+    // "12:8,11/11:10": per level the last stage of every phase after [1..4]
+    const std::string text(env);
+    size_t at = 0;
+    while (at < text.size()) {
+      size_t stop = text.find('/', at);
+      if (stop == std::string::npos) stop = text.size();
+      const std::string item = text.substr(at, stop - at);
+      const size_t colon = item.find(':');
+      if (colon != std::string::npos && std::atoi(item.substr(0, colon).c_str()) == k) {
+        size_t q = colon + 1;
+        while (q < item.size()) {
+          size_t comma = item.find(',', q);
+          if (comma == std::string::npos) comma = item.size();
+          ends.push_back(std::atoi(item.substr(q, comma - q).c_str()));
+          q = comma + 1;
+        }
+      }
+      at = stop + 1;
+    }
+  }
+  if (ends.empty()) {
+    // windows of at most 4 stages keep the groups at <= 48 rows, so that a tile can be 256 columns wide
+    ends = {std::min(8, k - 1)};
+    if (k - 1 > 8) ends.push_back(k - 1);
+  }
+  std::vector<std::pair<int, int>> ranges;
+  ranges.push_back({1, std::min(4, k - 1)});
+  int lo = 5;
+  for (int e : ends) {
+    if (e < lo || e > k - 1) throw std::runtime_error("SNFFT_WINDOWS: bad stage range");
+    ranges.push_back({lo, e});
+    lo = e + 1;
+  }
+  if (lo != k) throw std::runtime_error("SNFFT_WINDOWS: the ranges must end at stage k-1");
+  return ranges;
+}
 
 void build_host_plan(int n, HostPlan& plan) {
   if (n < 1 || n > kMaxN) throw std::runtime_error("n must be in 1..12");
@@ -481,6 +514,9 @@ void build_host_plan(int n, HostPlan& plan) {
       build_panel(plan, k, mu, L, coef_index, L.panels[mu]);
       if (k >= kPhaseMinLevel) build_phases(L.panels[mu]);
     }
+    // the phase kernel reads coefficient matrices in 16-byte pieces: keep the last one inside the pool
+    L.coef.push_back(0.0);
+    L.coef.push_back(0.0);
   }
 }
 

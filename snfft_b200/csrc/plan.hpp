@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace snfft {
@@ -51,32 +52,32 @@ struct alignas(16) Block {
 static_assert(sizeof(Block) == 32, "Block must be 32 bytes");
 
 // ---- row-group phases (levels >= 9) -------------------------------------------------------------
-// The k-1 stages of a level are cut into a few consecutive ranges ("phases").  Inside one phase the
-// rows of a panel fall into small groups that are closed under the phase's blocks (connected
-// components of "block touches row"; <= 48 rows for n <= 12), so a warp can load one group for 32
-// columns, run all its blocks and store it back: one coalesced pass over HBM per phase.
+// The k-1 stages of a level are cut into a few consecutive ranges ("phases", phase_ranges()).
+// Inside one phase the rows of a panel fall into groups that are closed under the phase's blocks
+// (connected components of "block touches row"), so a CTA can load a bundle of groups for a tile of
+// columns into shared memory, run all their blocks stage by stage and store them back: one
+// coalesced pass over HBM per phase.  Phase 0 is always stages 1..4 (generated in-place programs).
 struct PhaseRow {
   uint32_t xoff;   // offset of the row in the X-side buffer (its in-place slot), start of the run
   uint32_t dest;   // offset of the finished row in the spectrum-side buffer
   uint32_t final;  // 1: the row is finished in this phase (forward: store to dest; inverse: load from dest)
 };
-struct PhaseBlock {
-  uint8_t loc[kMaxBlock];  // rows of the block, as indices into the group's row list
+struct PhaseBlock {        // host only; the device form is BundleBlock (device_plan.hpp)
+  uint16_t loc[kMaxBlock];  // rows of the block, as indices into the group's row list
   uint8_t m;
-  uint8_t pad[2];
+  uint8_t stage;            // 1-based stage of the level
   uint32_t coef_f, coef_i;
 };
-static_assert(sizeof(PhaseBlock) == 16, "PhaseBlock must be 16 bytes");
 struct PhaseGroup {
-  uint32_t row_off, blk_off;  // into the level's row / block arrays of this phase
-  uint16_t nrows, nblk;
+  uint32_t row_off, blk_off;  // into the panel's row / block arrays of this phase
+  uint32_t nrows, nblk;
 };
 struct PanelPhase {
   int stage_lo = 0, stage_hi = 0;  // stages [lo, hi], 1-based
   std::vector<PhaseGroup> groups;  // row_off / blk_off relative to this panel's vectors
   std::vector<PhaseRow> rows;
   std::vector<uint32_t> row_slot;  // slot of every entry of `rows` (host only; shards remap offsets)
-  std::vector<PhaseBlock> blocks;
+  std::vector<PhaseBlock> blocks;  // per group: stage-major
   int max_rows = 0;
 };
 
@@ -127,7 +128,13 @@ struct HostPlan {
 void build_host_plan(int n, HostPlan& plan);
 
 constexpr int kPhaseMinLevel = 9;   // levels >= 9 run as row-group phases
-constexpr int kPhaseMaxRows = 64;   // rows of a group (shared-memory tile of a warp: rows x 32 columns)
+constexpr int kPhaseMaxRows = 448;  // rows of a group (shared-memory tile of a CTA: rows x 32 columns <= 112 KB)
+
+// Stage ranges of the phases of level k >= 9: [1..4] first, then the ranges given by their last
+// stages.  Default: 5..8 and 9..k-1 (groups of <= 48 rows, so that the tiles of the phase kernel can
+// be 256 columns wide); the environment variable SNFFT_WINDOWS overrides it for experiments, e.g.
+// "12:7,11/11:10" (per level the last stage of every phase after the first).
+std::vector<std::pair<int, int>> phase_ranges(int k);
 
 // Dense rho_lambda((j j+1)) for shape `irrep` of level k (row-major d*d), from lattice chains.
 void yor_trans_dense(const HostPlan& plan, int k, int irrep, int j, double* out);

@@ -26,7 +26,10 @@ from .young_tableau import FerrersDiagram
 _DEVICE = 0
 _MEMO = {}          # (kind, n, digest of the sampled values) -> packed spectrum (host)
 _MEMO_MAX = 8
-DIRECT_MAX_N = 8    # the [n!, n!] matrix of the direct sum is 13 GB at n = 8, 1 TB at n = 9
+# The direct sum is a GEMM with the [n!, n!] matrix of all rho_lambda(sigma): 203 MB at n = 7, 13 GB
+# at n = 8 (supported by Plan.dft_direct, released with Plan.dft_release), 1 TB at n = 9.  The
+# reference-shaped entry points keep the cached matrix small: n = 8 goes through the fast transform.
+DIRECT_MAX_N = 7
 
 
 def set_device(device: int) -> None:

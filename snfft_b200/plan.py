@@ -106,6 +106,31 @@ class Plan:
         return dict(d=d, m=m, stage=stage, slots=slots, final=final, coef_fwd=coef_f,
                     coef_inv=coef_i, dest=dest, rowbase=rowbase)
 
+    def export_coef(self, k: int) -> np.ndarray:
+        """Coefficient pool of level k (the matrices that block and phase tables index)."""
+        cnt = C.c_int64()
+        N.check(N.lib.snfft_export_coef(self._h, k, None, C.byref(cnt)))
+        coef = np.zeros(cnt.value, dtype=np.float64)
+        N.check(N.lib.snfft_export_coef(self._h, k, N.ptr(coef), C.byref(cnt)))
+        return coef
+
+    def export_phase(self, k: int, phase: int):
+        """Host copy of the device tables of one row-group phase of level k >= 9 (see
+        ``snfft_export_phase``): what ``phase_kernel`` executes, for CPU tests."""
+        sizes = np.zeros(10, dtype=np.int32)
+        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), None, None, None, None, None))
+        npan, nbun, nrows, nblk, nsf = (int(v) for v in sizes[:5])
+        panels = np.zeros((npan, 5), dtype=np.int32)
+        bundles = np.zeros((nbun, 4), dtype=np.int64)
+        rows = np.zeros((nrows, 3), dtype=np.int64)
+        blocks = np.zeros((nblk, 8), dtype=np.int32)
+        stage_first = np.zeros(nsf, dtype=np.int32)
+        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), N.ptr(panels), N.ptr(bundles),
+                                         N.ptr(rows), N.ptr(blocks), N.ptr(stage_first)))
+        return dict(panels=panels, bundles=bundles, rows=rows, blocks=blocks, stage_first=stage_first,
+                    cols_per_lane=int(sizes[5]), nstages=int(sizes[6]), max_rows=int(sizes[7]),
+                    stage_lo=int(sizes[8]), nphases=int(sizes[9]))
+
     # ------------------------------------------------------------------ device transforms
     def _check(self, t, name, last=None):
         import torch
@@ -188,7 +213,9 @@ class Plan:
         return out
 
     def dft_direct(self, f):
-        """Direct-sum transform as one DMMA GEMM (n <= 7); f in lexicographic order."""
+        """Direct-sum transform as one DMMA GEMM (n <= 8); f in lexicographic order.  The [n!, n!]
+        matrix of all rho_lambda(sigma) is built on first use and stays in the plan (13 GB at
+        n = 8) until ``dft_release()``."""
         import torch
         self._check(f, "f", self.size)
         out = torch.empty_like(f)
@@ -196,6 +223,10 @@ class Plan:
             N.check(N.lib.snfft_dft_direct(self._h, N.ptr(f), N.ptr(out), f.numel() // self.size,
                                            self._stream()))
         return out
+
+    def dft_release(self):
+        """Free the direct-sum matrix that ``dft_direct`` cached in this plan."""
+        N.check(N.lib.snfft_dft_release(self._h))
 
     def roundtrip_host(self, f_host, fhat_host=None, back_host=None, order: str = "coset",
                        chunks: int = 8, streams: int = 4):
@@ -267,7 +298,8 @@ def launch_count() -> int:
     return int(N.lib.snfft_launch_count())
 
 
-KERNEL_KINDS = ("fused_fwd", "fused_inv", "level_fwd", "level_inv", "reorder", "yor", "dgemm", "other")
+KERNEL_KINDS = ("fused_fwd", "fused_inv", "level8_fwd", "level8_inv", "level_table", "p1", "p0", "phase_fwd",
+                "phase_inv", "exchange", "reorder", "yor", "dgemm", "other")
 
 
 def timing_enable(on: bool) -> None:

@@ -292,36 +292,93 @@ class ShardedPlan:
             return True
         if self.world == 1 or self.world > 16 or dist.get_backend(self.group) != 'nccl':
             return False
+        group = self.group if self.group is not None else dist.group.WORLD
+        dev = torch.device('cuda', self.device)
+        state = None
         try:
             import torch.distributed._symmetric_memory as symm
-            group = self.group if self.group is not None else dist.group.WORLD
-            dev = torch.device('cuda', self.device)
-            columns = symm.empty(self.column_buffer_elements(), dtype=torch.float64, device=dev)
-            hc = symm.rendezvous(columns, group)
-            self._p2p = dict(columns=columns, hc=hc, ptrs=[int(p) for p in hc.buffer_ptrs])
+            cols, _local, _work, pad_words = self.workspace_sizes()
+            pad = (pad_words + 31) // 32 * 32      # keep the column buffer 256-byte aligned
+            buf = symm.empty(pad + cols, dtype=torch.float64, device=dev)
+            hc = symm.rendezvous(buf, group)
+            buf[:pad].zero_()                       # signal pad: epochs only grow from zero
+            torch.cuda.synchronize(dev)
+            ptrs = [int(p) for p in hc.buffer_ptrs]
+            state = dict(buffer=buf, hc=hc, columns=buf[pad:], ptrs=[p + 8 * pad for p in ptrs],
+                         wsk=self.make_workspace([p + 8 * pad for p in ptrs], ptrs))
         except Exception as exc:  # no symmetric memory here: keep the NCCL path
-            self._p2p = None
             self._p2p_error = repr(exc)
+        # every rank must take the same exchange: agree on the outcome (a rank whose allocation
+        # failed would otherwise wait in all_to_all while the others wait in the peer barrier)
+        flag = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self._p2p = None
             return False
+        dist.barrier(group=group)   # every pad is zeroed before anybody raises a flag
+        self._p2p = state
         return True
 
+    # ------------------------------------------------------------------ whole schedule in C
+    def workspace_sizes(self):
+        """(column buffer, local, shard work, signal pad words): see ``snfft_shard_ws_sizes``."""
+        sizes = (C.c_int64 * 4)()
+        N.check(N.lib.snfft_shard_ws_sizes(self._h, sizes))
+        return [int(v) for v in sizes]
+
+    def make_workspace(self, col_ptrs, pad_ptrs):
+        """The persistent workspace of ``snfft_forward_sharded`` / ``snfft_inverse_sharded``:
+        col_ptrs[r] / pad_ptrs[r] = device pointers of rank r's column-shard buffer and signal pad
+        that THIS process can dereference (symmetric memory / CUDA IPC; plain allocations when all
+        ranks live in one process).  Local and shard scratch buffers are allocated here, once."""
+        import torch
+        dev = torch.device('cuda', self.device)
+        cols, local, work, _pad = self.workspace_sizes()
+        ws = N.ShardWorkspace()
+        for r in range(self.world):
+            ws.peer_cols[r] = int(col_ptrs[r])
+            ws.peer_pads[r] = int(pad_ptrs[r])
+        keep = dict(local_a=torch.empty(max(2, local), dtype=torch.float64, device=dev),
+                    local_b=torch.empty(max(2, local), dtype=torch.float64, device=dev),
+                    shard_a=torch.empty(max(2, work), dtype=torch.float64, device=dev),
+                    shard_b=torch.empty(max(2, work), dtype=torch.float64, device=dev),
+                    status=torch.zeros(1, dtype=torch.int32, device=dev))
+        for name, t in keep.items():
+            setattr(ws, name, t.data_ptr())
+        keep['ws'] = ws
+        return keep
+
+    def forward_c(self, f_local, wsk, out=None):
+        """``snfft_forward_sharded`` on the current stream: the whole forward schedule of this rank."""
+        import torch
+        if out is None:
+            out = torch.empty(self.sizes[self.rank][self.n], dtype=torch.float64, device=f_local.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.snfft_forward_sharded(self._h, N.ptr(f_local), N.ptr(out), C.byref(wsk['ws']),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def inverse_c(self, compact, wsk, out=None):
+        """``snfft_inverse_sharded`` on the current stream."""
+        import torch
+        if out is None:
+            b, e = self.local_elements()
+            out = torch.empty(e - b, dtype=torch.float64, device=compact.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.snfft_inverse_sharded(self._h, N.ptr(compact), N.ptr(out), C.byref(wsk['ws']),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def barrier_timed_out(self):
+        """True if a device-side barrier of this rank gave up waiting for a peer (synchronises)."""
+        p = getattr(self, '_p2p', None)
+        return bool(p and int(p['wsk']['status'].item()) != 0)
+
     def forward_p2p(self, f_local):
-        p = self._p2p
-        spectra = self.forward_local_spectra(f_local)
-        p['hc'].barrier(channel=0)          # nobody still reads its column buffer
-        self.forward_push(spectra, p['ptrs'])
-        p['hc'].barrier(channel=1)          # every rank has pushed: my columns are complete
-        return self.forward_finish_columns(p['columns'])
+        return self.forward_c(f_local, self._p2p['wsk'])
 
     def inverse_p2p(self, compact):
-        p = self._p2p
-        x = compact
-        for k in range(self.n, self.m + 1, -1):
-            x = self._level(k, x, True)
-        p['hc'].barrier(channel=0)          # nobody still pulls from my column buffer
-        self._level(self.m + 1, x, True, out=p['columns'])
-        p['hc'].barrier(channel=1)          # every rank's columns are complete
-        return self.inverse_finish_pull(p['ptrs'])
+        return self.inverse_c(compact, self._p2p['wsk'])
 
     def gather_spectrum(self, compact):
         """Full packed spectrum assembled on every rank (for checks; moves the whole spectrum)."""

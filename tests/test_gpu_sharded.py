@@ -78,6 +78,42 @@ def test_peer_memory_exchange_on_one_gpu(n, world, split):
         assert ((back - coset[b:e]).norm() / coset[b:e].norm()).item() < 1e-10
 
 
+@pytest.mark.parametrize('n,world,split', [(6, 2, 4), (8, 3, 5), (9, 4, 7), (10, 8, 7), (10, 5, 8), (9, 2, 8)])
+def test_whole_schedule_in_c_virtual_world(n, world, split):
+    """snfft_forward_sharded / snfft_inverse_sharded (the whole schedule of a rank behind one C
+    call, device-side barriers between the ranks) with all ranks of a virtual world in one
+    process: one stream per rank, "peer" pointers are ordinary device pointers."""
+    nf = math.factorial(n)
+    coset = torch.randn(nf, dtype=torch.float64, device='cuda',
+                        generator=torch.Generator(device='cuda').manual_seed(3 * n + world))
+    ranks = [ShardedPlan(n, r, world, device=0, split=split) for r in range(world)]
+    cols_elems, _, _, pad_words = ranks[0].workspace_sizes()
+    assert all(sp.workspace_sizes()[0] == cols_elems for sp in ranks)    # symmetric allocation
+    cols = [torch.full((cols_elems,), float('nan'), dtype=torch.float64, device='cuda') for _ in ranks]
+    pads = [torch.zeros(pad_words, dtype=torch.int64, device='cuda') for _ in ranks]
+    wsk = [sp.make_workspace([t.data_ptr() for t in cols], [t.data_ptr() for t in pads]) for sp in ranks]
+    streams = [torch.cuda.Stream() for _ in ranks]
+    torch.cuda.synchronize()
+    for rep in range(2):                                # twice: the barrier epochs keep counting
+        compact, back = [None] * world, [None] * world
+        for q, sp in enumerate(ranks):
+            with torch.cuda.stream(streams[q]):
+                compact[q] = sp.forward_c(coset[slice(*sp.local_elements())], wsk[q])
+        torch.cuda.synchronize()
+        for q, sp in enumerate(ranks):
+            with torch.cuda.stream(streams[q]):
+                back[q] = sp.inverse_c(compact[q], wsk[q])
+        torch.cuda.synchronize()
+        assert all(int(k['status'].item()) == 0 for k in wsk), 'a device-side barrier timed out'
+        # identical to the pack / hand-over / unpack path of the Python driver
+        sends = [sp.forward_local(coset[slice(*sp.local_elements())]) for sp in ranks]
+        for q, sp in enumerate(ranks):
+            want = sp.forward_finish([sends[r][q] for r in range(world)])
+            assert torch.equal(compact[q], want)
+            b, e = sp.local_elements()
+            assert ((back[q] - coset[b:e]).norm() / coset[b:e].norm()).item() < 1e-10
+
+
 def _nccl_worker(rank, world, n, port, ret):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist

@@ -205,3 +205,97 @@ def test_reorder_tile_factorisation():
             base += smaller * fact[n - a_]
         assert c2l[top + flat] == base + A
 
+
+
+def interpret_level_by_phases(plan, k, x, inverse=False):
+    """Level k >= 9 the way the device runs it: stages 1..4 in place on the X side (export_panel
+    blocks; on the device these are the generated programs plus the finished-row move), then every
+    row-group phase from the exported BUNDLE tables (what phase_kernel executes): per bundle load
+    its rows, run the blocks stage by stage, store rows in place or - when finished - to the
+    spectrum.  x: [k, (k-1)!] forward, [k!] inverse."""
+    parts, dims, offs = plan.layout(k - 1)
+    kf = math.factorial(k)
+    coef = plan.export_coef(k)
+    nphases = plan.export_phase(k, 1)['nphases']
+    phases = [plan.export_phase(k, ph) for ph in range(1, nphases)]
+    xs = np.zeros(kf) if inverse else x.reshape(-1).copy()
+    ss = x.reshape(-1).copy() if inverse else np.zeros(kf)
+
+    def low_stages(inv):
+        for pi, d in enumerate(dims):
+            prog = plan.export_panel(k, pi)
+            low = [b for b in range(len(prog['m'])) if prog['stage'][b] <= 4]
+            last = {}
+            for b in range(len(prog['m'])):
+                for a in range(prog['m'][b]):
+                    last[prog['slots'][b, a]] = b
+            done_low = [s for s in range(k * d) if prog['stage'][last[s]] <= 4]
+            touched = sorted({int(v) for b in low for v in prog['slots'][b, :prog['m'][b]]})
+            buf = {}
+            for s in touched:
+                src = ss[prog['dest'][s]:prog['dest'][s] + d] if (inv and s in done_low) else \
+                    xs[prog['rowbase'][s]:prog['rowbase'][s] + d]
+                buf[s] = src.copy()
+            for b in (reversed(low) if inv else low):
+                m = prog['m'][b]
+                sl = [int(v) for v in prog['slots'][b, :m]]
+                cm = prog['coef_inv' if inv else 'coef_fwd'][b, :m * m].reshape(m, m)
+                res = cm @ np.stack([buf[s] for s in sl])
+                for a, s in enumerate(sl):
+                    buf[s] = res[a]
+            for s in touched:
+                if not inv and s in done_low:
+                    ss[prog['dest'][s]:prog['dest'][s] + d] = buf[s]
+                else:
+                    xs[prog['rowbase'][s]:prog['rowbase'][s] + d] = buf[s]
+
+    def run_phase(T, inv):
+        assert T['max_rows'] * 32 * T['cols_per_lane'] * 8 <= 112 * 1024
+        ns = T['nstages']
+        for pi, (d, tiles, b_off, nb, pack) in enumerate(T['panels']):
+            assert d == dims[pi]
+            for bu in range(b_off, b_off + nb):
+                row_off, blk_off, st_off, nrows = (int(v) for v in T['bundles'][bu])
+                rows = T['rows'][row_off:row_off + nrows]
+                buf = np.stack([(ss[r[1]:r[1] + d] if (inv and r[2]) else xs[r[0]:r[0] + d]).copy() for r in rows])
+                sf = T['stage_first'][st_off:st_off + ns * 17].reshape(ns, 17)   # per stage: ranges of 16 warps
+                assert (np.diff(sf.reshape(-1)) >= 0).all()
+                for st in (range(ns - 1, -1, -1) if inv else range(ns)):
+                    seen = set()
+                    for b in range(blk_off + sf[st, 0], blk_off + sf[st, 16]):
+                        m = T['blocks'][b, 5]
+                        loc = [int(v) for v in T['blocks'][b, :m]]
+                        assert not (seen & set(loc)), 'blocks of one stage must touch disjoint rows'
+                        seen |= set(loc)
+                        at = T['blocks'][b, 7 if inv else 6]
+                        buf[loc] = coef[at:at + m * m].reshape(m, m) @ buf[loc]
+                for r, v in zip(rows, buf):
+                    if not inv and r[2]:
+                        ss[r[1]:r[1] + d] = v
+                    else:
+                        xs[r[0]:r[0] + d] = v
+
+    if not inverse:
+        low_stages(False)
+        for T in phases:
+            run_phase(T, False)
+        return ss
+    for T in reversed(phases):
+        run_phase(T, True)
+    low_stages(True)
+    return xs.reshape(k, kf // k)
+
+
+@pytest.mark.parametrize('windows', [None, '9:6,8'])
+def test_phase_bundle_tables_reproduce_level_9(windows, monkeypatch):
+    """The bundle tables of the row-group phases (device layout) against the plain block programs."""
+    if windows:
+        monkeypatch.setenv('SNFFT_WINDOWS', windows)
+    k = 9
+    plan = Plan(k, -1)
+    x = np.random.default_rng(9).standard_normal((k, math.factorial(k - 1)))
+    ref = interpret_level(plan, k, x)
+    got = interpret_level_by_phases(plan, k, x)
+    assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
+    back = interpret_level_by_phases(plan, k, ref, inverse=True)
+    assert np.abs(back - x).max() < 1e-11
