@@ -122,6 +122,15 @@ int snfft_coset_to_lex_host(const snfft_plan* plan, int64_t* out_host);
 int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
               double* out_dev, void* stream);
 
+/* Sampled inverse: f(sigma_j) for `count` permutations straight from ONE packed spectrum,
+ * f(sigma) = (1/n!) sum_lambda d_lambda tr(rho_lambda(sigma)^T f_hat(lambda))
+ * (tile/par_inv_ft.py:27-45 summed over the irreps; the per-state evaluation of
+ * compute_policy.py:66-88).  All irreps in one launch; rho is never materialised (the generator
+ * word of sigma is applied to the rows of f_hat(lambda) as 2-sparse rotations).
+ * perms_dev int32[count][n] 1-based tuples, out_dev double[count]. */
+int snfft_inverse_at(const snfft_plan* plan, const double* fhat_dev, const int32_t* perms_dev, int64_t count,
+                     double* out_dev, void* stream);
+
 /* Direct sum f_hat = sum_sigma f(sigma) rho_lambda(sigma) for every lambda (fft.py:115-151
  * `fourier_transform{,2}`) as one dense fp64 GEMM [batch, n!] x [n!, n!] on the DMMA pipe; the
  * [n!, n!] matrix of all rho_lambda(sigma) is built on the device on first use.  n <= 8 (13 GB at n = 8).
@@ -224,6 +233,14 @@ int snfft_inverse_sharded(snfft_shard* shard, const double* fhat_compact_dev, do
  * sums over orientations (wreath.py:43-58) are evaluated as such products. */
 int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t m, int64_t n, int64_t k,
                 void* stream);
+/* Character sums over the orientations (wreath.py:43-58, :123-143) as a DFT over C_3^m: every row
+ * of in_re [count][3^m] (orientation index = base-3 number of the tuple, first letter most
+ * significant) is transformed with m radix-3 passes in shared memory and only the nfreq frequencies
+ * listed in freq_dev (same indexing) are written: out[count][nfreq] = sum_o in[o] omega^{+k.o}.
+ * inverse != 0 is the adjoint: in [count][nfreq] complex is scattered onto the frequency grid and
+ * out [count][3^m] = sum_k in[k] omega^{-k.o} (no normalisation).  m <= 9. */
+int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
+                 int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream);
 /* dst[e][0..width) = src[idx[e]][0..width) for e < count: regroups S_n by cosets of a Young
  * subgroup (the double loop over coset representatives of wreath.py:304-313 as an index map). */
 int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev, int64_t count, int width,
@@ -244,13 +261,13 @@ int64_t snfft_launch_count(void);
 int snfft_debug_force_table_driven(int on);
 
 /* Per-kernel timing for bench.py: when enabled, every launch of this library is bracketed by CUDA
- * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[14] and
- * launches_by_kind[14] and resets the totals.  Kinds: 0 fused forward (levels 2..7), 1 fused
+ * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[15] and
+ * launches_by_kind[15] and resets the totals.  Kinds: 0 fused forward (levels 2..7), 1 fused
  * inverse, 2 level 8 forward (generated), 3 level 8 inverse, 4 table-driven level kernel,
  * 5 in-place stages 1..4 of a level >= 9, 6 finished-row move of those levels, 7 row-group phase
- * forward, 8 row-group phase inverse, 9 peer-memory exchange, 10 reorder, 11 yor, 12 dgemm,
- * 13 other. */
-#define SNFFT_NUM_KERNEL_KINDS 14
+ * forward, 8 row-group phase inverse, 9 peer-memory exchange, 10 device-side barrier between
+ * ranks (includes waiting for the slowest rank), 11 reorder, 12 yor, 13 dgemm, 14 other. */
+#define SNFFT_NUM_KERNEL_KINDS 15
 int snfft_timing_enable(int on);
 int snfft_timing_read(double* ms_by_kind, int64_t* launches_by_kind);
 
@@ -269,16 +286,17 @@ int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_bloc
 
 /* Host-side export of the device tables of one row-group phase of level k >= 9 (phase >= 1; phase 0
  * is stages 1..4, generated programs), so that CPU tests can interpret exactly what the phase
- * kernel executes.  sizes int32[10] = {panels, bundles, rows, blocks, stage_first entries,
- * columns per lane, stages, rows of the largest bundle, first stage, phases of the level}; the
- * other buffers may be NULL to query sizes: panels int32[..][5] = {columns, tiles, first bundle,
- * bundles, pack}; bundles int64[..][4] = {first row, first block, first stage_first entry, rows};
- * rows int64[..][3] = {x-side offset, spectrum offset, finished flag}; blocks int32[..][8] =
- * {row 0..4 (-1 padded, bundle-relative), m, forward coef offset, inverse coef offset};
- * stage_first int32[bundles][stages][17]: per stage the block ranges of the 16 warps of a CTA
- * (warp w runs blocks [w], [w+1]), bundle-relative). */
+ * kernel executes.  sizes int32[8] = {panels, groups, 16-byte words of a blob array, rows of the
+ * largest group, words of the largest blob, stages, first stage, phases of the level}; the other
+ * buffers may be NULL to query sizes: panels int32[..][5] = {columns, tiles, first group, groups,
+ * pack}; groups int64[..][4] = {first word of the blob, words, rows, rows that stay on the x side
+ * (they come first)}; blob_fwd / blob_inv: the program blobs (16 x words bytes each).  A blob is
+ * u32 xoff[rows], u32 dest[rows], padding to 16 bytes, then per block a 16-byte header {u16 byte
+ * offset (row index * 256) of its rows [5], u16 m, u32 0} followed by the m x m matrix (doubles,
+ * row-major, y = C x in place on the rows; padded to 16 bytes), terminated by a header with m = 0;
+ * the inverse blob lists the blocks backwards with the inverse matrices. */
 int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes, int32_t* panels,
-                       int64_t* bundles, int64_t* rows, int32_t* blocks, int32_t* stage_first);
+                       int64_t* groups, void* blob_fwd, void* blob_inv);
 /* The coefficient pool of level k that the block / phase tables index (doubles). */
 int snfft_export_coef(const snfft_plan* plan, int k, double* coef, int64_t* count);
 

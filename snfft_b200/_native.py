@@ -58,6 +58,7 @@ SIGNATURES = {
     "snfft_reorder": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_coset_to_lex_host": (C.c_int, [_p, _p]),
     "snfft_yor": (C.c_int, [_p, C.c_int, _p, C.c_int64, _p, _p]),
+    "snfft_inverse_at": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p]),
     "snfft_dft_direct": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
     "snfft_dft_release": (C.c_int, [_p]),
     "snfft_shard_create": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "snfft_forward_sharded": (C.c_int, [_p, _p, _p, _p, _p]),
     "snfft_inverse_sharded": (C.c_int, [_p, _p, _p, _p, _p]),
     "snfft_dgemm": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _p]),
+    "snfft_c3_dft": (C.c_int, [C.c_int, _p, _p, _p, C.c_int, C.c_int64, _p, _p, C.c_int, _p]),
     "snfft_gather": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_plan_device_bytes": (C.c_int64, [_p]),
     "snfft_level_macs_per_element": (C.c_double, [_p, C.c_int]),
@@ -82,7 +84,7 @@ SIGNATURES = {
     "snfft_timing_enable": (C.c_int, [C.c_int]),
     "snfft_timing_read": (C.c_int, [_p, _p]),
     "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "snfft_export_phase": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
+    "snfft_export_phase": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
     "snfft_export_coef": (C.c_int, [_p, C.c_int, _p, _p]),
 }
 

@@ -56,9 +56,8 @@ struct DeviceGuard {
 
 // device tables of one row-group phase plus the host copies the launcher needs
 struct PhaseHost {
-  BundleDev dev{};
-  std::vector<int32_t> items;  // per panel: bundles * tiles
-  std::vector<int32_t> pack;   // per panel
+  PhaseDev dev{};
+  std::vector<int32_t> groups, tiles, pack;  // per panel
 };
 
 struct YorTables {
@@ -84,6 +83,10 @@ struct snfft_plan {
   uint32_t* lex_table = nullptr;
   std::mutex lazy_mu;
   std::map<int, YorTables> yor_tables;
+  InvAtItem* inv_at_items = nullptr;    // sampled inverse (snfft_inverse_at): lazily built under lazy_mu
+  InvAtIrrep* inv_at_irreps = nullptr;
+  int inv_at_nitems = 0;
+  size_t inv_at_smem = 0;
   std::mutex dft_mu;             // guards dft_matrix (lazily built; released by snfft_dft_release)
   double* dft_matrix = nullptr;
 
@@ -208,200 +211,101 @@ struct LevelLayout {
   int64_t lgroups_hint = 1;  // groups of the level in a whole transform of one function (n!/k!)
 };
 
-// Shared-memory budget of a phase CTA (default: two CTAs per SM); SNFFT_BUNDLE_KB overrides it for
-// experiments.
-int64_t bundle_smem_bytes() {
-  if (const char* env = std::getenv("SNFFT_BUNDLE_KB")) {
-    const int kb = std::atoi(env);
-    if (kb >= 16 && kb <= 224) return (int64_t)kb * 1024;
-  }
-  return 112 * 1024;
-}
-constexpr int kPhaseWarpsHost = 16;  // warps of a phase CTA (kernels.cu: kPhaseWarps)
-
+// Device tables of the row-group phases of one level for a given layout (whole transform or column
+// shard): per group a program blob, see device_plan.hpp.
 template <class Uploader>
-void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, const double* coef, Uploader&& up,
+void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, Uploader&& up,
                       std::vector<PhaseHost>& out_devs) {
   if (prog.panels.empty() || prog.panels[0].phases.empty()) return;
   const size_t nphases = prog.panels[0].phases.size();
-  const int64_t kBundleSmemBytes = bundle_smem_bytes();
   out_devs.push_back(PhaseHost{});  // phase 0 (stages 1..4) runs as generated programs: placeholder
   for (size_t ph = 1; ph < nphases; ++ph) {
     const int stage_lo = prog.panels[0].phases[ph].stage_lo, stage_hi = prog.panels[0].phases[ph].stage_hi;
-    const int nstages = stage_hi - stage_lo + 1;
-    int max_group = 1;
-    for (size_t p = 0; p < prog.panels.size(); ++p)
-      if (lay.width[p] > 0) max_group = std::max(max_group, prog.panels[p].phases[ph].max_rows);
-    // more columns per lane amortise the per-block descriptor and coefficient reads (the kernel is
-    // bound by its instruction count, not by HBM); the two tiles [rows of a bundle][32 * cpl columns]
-    // have to fit shared memory, and on narrow panels (column shards) lanes without a column are
-    // paid for
-    int cpl_max = 1;
-    while (cpl_max < 8 && (int64_t)max_group * 64 * cpl_max * 8 <= kBundleSmemBytes) cpl_max *= 2;
-    if ((int64_t)max_group * 32 * 8 > kBundleSmemBytes) throw std::runtime_error("phase group does not fit in shared memory");
-    int cpl = 1;
-    {
-      const double speed[9] = {0, 0.35, 0.55, 0, 0.8, 0, 0, 0, 1.0};
-      double best = -1;
-      for (int c = 1; c <= cpl_max; c *= 2) {
-        double used = 0, paid = 0;
-        for (size_t p = 0; p < prog.panels.size(); ++p) {
-          const double nr = (double)prog.panels[p].phases[ph].rows.size();
-          const int w = lay.width[p];
-          if (w == 0) continue;
-          const int W = 32 * c;
-          used += nr * w;
-          // narrow panels share a tile between members of the group loop when there are several
-          paid += (2 * w <= W && lay.lgroups_hint > 1) ? nr * w * ((double)W / (W / w * w))
-                                                       : nr * ((w + W - 1) / W) * W;
-        }
-        const double score = paid > 0 ? speed[c] * used / paid : 0;
-        if (score > best) {
-          best = score;
-          cpl = c;
-        }
-      }
-    }
-    const int W = 32 * cpl;
-    const int cap_rows = (int)(kBundleSmemBytes / ((int64_t)W * 8));
-    std::vector<BundlePanelDev> panels;
-    std::vector<Bundle> bundles;
-    std::vector<uint32_t> row_xoff, row_dest;
-    std::vector<BundleBlock> blocks_f, blocks_i;
-    std::vector<uint32_t> stage_first;
-    int64_t items = 0;
-    int max_rows = 1;
+    std::vector<PhasePanelDev> panels;
+    std::vector<PhaseGroupDev> groups;
+    std::vector<U128> blob_f, blob_i;
+    int max_rows = 1, max_blob = 1;
+    PhaseHost H;
+    auto push_words = [](std::vector<U128>& v, const void* src, size_t bytes) {
+      const size_t words = (bytes + 15) / 16;
+      const size_t at = v.size();
+      v.resize(at + words, U128{0, 0, 0, 0});
+      std::memcpy(&v[at], src, bytes);
+    };
     for (size_t p = 0; p < prog.panels.size(); ++p) {
       const PanelProgram& P = prog.panels[p];
       const PanelPhase& pp = P.phases[ph];
       const int w = lay.width[p];
-      BundlePanelDev pd;
+      PhasePanelDev pd;
       pd.d = w;
-      pd.pack = (w > 0 && 2 * w <= W) ? W / w : 1;
-      pd.tiles = pd.pack > 1 ? 1 : (w + W - 1) / W;
+      pd.pack = (w > 0 && w <= 16) ? 32 / w : 1;
+      pd.tiles = pd.pack > 1 ? 1 : (w + 31) / 32;
       pd.magic = w > 0 ? (65536 + w - 1) / w : 0;
-      pd.bundle_off = (int32_t)bundles.size();
-      pd.nbundles = 0;
-      pd.item_off = items;
-      if (w > 0) {
-        size_t g = 0;
-        while (g < pp.groups.size()) {
-          // as many whole groups as fit the tile
-          size_t g1 = g;
-          int nr = 0;
-          while (g1 < pp.groups.size() && (g1 == g || nr + (int)pp.groups[g1].nrows <= cap_rows)) {
-            nr += (int)pp.groups[g1].nrows;
-            ++g1;
-          }
-          Bundle B;
-          B.row_off = (uint32_t)row_xoff.size();
-          B.blk_off = (uint32_t)blocks_f.size();
-          B.stage_off = (uint32_t)stage_first.size();
-          max_rows = std::max(max_rows, nr);
-          // rows of the bundle: those that stay on the x side first, then the ones finished in this
-          // phase (neither the load nor the store loop of the kernel selects a buffer per row)
-          std::vector<int> base(g1 - g);       // first row of every group in group order
-          std::vector<int> place((size_t)nr);  // group-order row -> position inside the bundle
-          {
-            int at = 0, nlow = 0;
-            for (size_t q = g; q < g1; ++q) {
-              const PhaseGroup& G = pp.groups[q];
-              base[q - g] = at;
-              for (uint32_t r = 0; r < G.nrows; ++r) nlow += pp.rows[G.row_off + r].final ? 0 : 1;
-              at += (int)G.nrows;
-            }
-            int lo_at = 0, hi_at = nlow;
-            at = 0;
-            row_xoff.resize(row_xoff.size() + nr);
-            row_dest.resize(row_dest.size() + nr);
-            for (size_t q = g; q < g1; ++q) {
-              const PhaseGroup& G = pp.groups[q];
-              for (uint32_t r = 0; r < G.nrows; ++r, ++at) {
-                const uint32_t slot = pp.row_slot[G.row_off + r];
-                const int pos = pp.rows[G.row_off + r].final ? hi_at++ : lo_at++;
-                place[at] = pos;
-                row_xoff[B.row_off + pos] = lay.rowbase[p][slot];
-                row_dest[B.row_off + pos] = lay.dest[p][slot];
-              }
-            }
-            B.nrows = (uint32_t)nr | ((uint32_t)nlow << 16);
-          }
-          uint32_t nb = 0;
-          for (int st = stage_lo; st <= stage_hi; ++st) {
-            // the blocks of the stage, sorted by (size, coefficient matrix): a warp works through a
-            // consecutive range and keeps the matrix in registers over a run of equal blocks
-            struct Item {
-              BundleBlock f;
-              uint32_t coef_i;
-            };
-            std::vector<Item> its;
-            for (size_t q = g; q < g1; ++q) {
-              const PhaseGroup& G = pp.groups[q];
-              for (uint32_t b = 0; b < G.nblk; ++b) {
-                const PhaseBlock& pb = pp.blocks[G.blk_off + b];
-                if (pb.stage != st) continue;
-                Item it{};
-                it.f.m = pb.m;
-                for (int a = 0; a < pb.m; ++a) it.f.loc[a] = (uint16_t)place[pb.loc[a] + base[q - g]];
-                it.f.coef = pb.coef_f;
-                it.coef_i = pb.coef_i;
-                its.push_back(it);
-              }
-            }
-            std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) {
-              return a.f.m != b.f.m ? a.f.m > b.f.m : a.f.coef < b.f.coef;
-            });
-            // ranges of the 16 warps, balanced by cost (m^2 multiply-adds + 2 m shared-memory accesses + overhead)
-            auto cost = [](const Item& it) { return (int64_t)it.f.m * it.f.m + 2 * it.f.m + 6; };
-            int64_t total = 0;
-            for (const Item& it : its) total += cost(it);
-            int64_t acc = 0;
-            size_t at2 = 0;
-            for (int w = 0; w < kPhaseWarpsHost; ++w) {
-              stage_first.push_back(nb + (uint32_t)at2);
-              const int64_t target = total * (w + 1) / kPhaseWarpsHost;
-              while (at2 < its.size() && acc + cost(its[at2]) / 2 < target) acc += cost(its[at2++]);
-            }
-            at2 = its.size();
-            for (const Item& it : its) {
-              BundleBlock bb = it.f;
-              blocks_f.push_back(bb);
-              bb.coef = it.coef_i;
-              blocks_i.push_back(bb);
-            }
-            nb += (uint32_t)its.size();
-            stage_first.push_back(nb);
-          }
-          bundles.push_back(B);
-          ++pd.nbundles;
-          g = g1;
-        }
-      }
-      items += (int64_t)pd.nbundles * pd.tiles;
+      pd.grp_off = (int32_t)groups.size();
+      pd.ngroups = w > 0 ? (int32_t)pp.groups.size() : 0;
       panels.push_back(pd);
+      H.groups.push_back(pd.ngroups);
+      H.tiles.push_back(pd.tiles);
+      H.pack.push_back(pd.pack);
+      if (w == 0) continue;
+      for (const PhaseGroup& G : pp.groups) {
+        const int nr = (int)G.nrows;
+        if (nr > 64) throw std::runtime_error("phase group has more than 64 rows (row table of the phase kernel)");
+        max_rows = std::max(max_rows, nr);
+        // rows that stay on the x side first, then the ones finished in this phase
+        std::vector<int> place(nr);
+        int nlow = 0;
+        for (int r = 0; r < nr; ++r) nlow += pp.rows[G.row_off + r].final ? 0 : 1;
+        std::vector<uint32_t> table(2 * (size_t)nr, 0);
+        int lo_at = 0, hi_at = nlow;
+        for (int r = 0; r < nr; ++r) {
+          const uint32_t slot = pp.row_slot[G.row_off + r];
+          const int pos = pp.rows[G.row_off + r].final ? hi_at++ : lo_at++;
+          place[r] = pos;
+          table[pos] = lay.rowbase[p][slot];
+          table[nr + pos] = lay.dest[p][slot];
+        }
+        PhaseGroupDev gd;
+        gd.blob_off = (uint32_t)blob_f.size();
+        gd.nrows = (uint32_t)nr | ((uint32_t)nlow << 16);
+        gd.reserved = 0;
+        for (int dir = 0; dir < 2; ++dir) {
+          std::vector<U128>& out = dir ? blob_i : blob_f;
+          push_words(out, table.data(), table.size() * sizeof(uint32_t));
+          for (uint32_t bq = 0; bq < G.nblk; ++bq) {
+            // forward: stage order; inverse: the same blocks backwards with the inverse matrices
+            const PhaseBlock& pb = pp.blocks[G.blk_off + (dir ? G.nblk - 1 - bq : bq)];
+            if (pb.stage < stage_lo || pb.stage > stage_hi) throw std::runtime_error("block outside its phase");
+            uint16_t off[kMaxBlock] = {0, 0, 0, 0, 0};
+            for (int a = 0; a < pb.m; ++a) off[a] = (uint16_t)(place[pb.loc[a]] * 256);
+            U128 h;
+            h.x = off[0] | ((uint32_t)off[1] << 16);
+            h.y = off[2] | ((uint32_t)off[3] << 16);
+            h.z = off[4] | ((uint32_t)pb.m << 16);
+            h.w = 0;
+            out.push_back(h);
+            push_words(out, &prog.coef[dir ? pb.coef_i : pb.coef_f], (size_t)pb.m * pb.m * sizeof(double));
+          }
+          out.push_back(U128{0, 0, 0, 0});  // terminator (m = 0)
+        }
+        if (blob_f.size() != blob_i.size()) throw std::runtime_error("blob size mismatch");
+        gd.blob_len = (uint32_t)blob_f.size() - gd.blob_off;
+        max_blob = std::max(max_blob, (int)gd.blob_len);
+        groups.push_back(gd);
+      }
     }
-    BundleDev D;
+    PhaseDev D;
     D.panels = up(panels);
-    D.bundles = up(bundles);
-    D.row_xoff = up(row_xoff);
-    D.row_dest = up(row_dest);
-    D.blocks_f = up(blocks_f);
-    D.blocks_i = up(blocks_i);
-    D.stage_first = up(stage_first);
-    D.coef = coef;
-    D.nitems = items;
+    D.groups = up(groups);
+    D.blob_f = up(blob_f);
+    D.blob_i = up(blob_i);
     D.in_stride = lay.in_stride;
     D.out_stride = lay.out_stride;
     D.npanels = (int32_t)panels.size();
     D.max_rows = max_rows;
-    D.cols_per_lane = cpl;
-    D.nstages = nstages;
-    PhaseHost H;
+    D.max_blob = max_blob;
+    D.nstages = stage_hi - stage_lo + 1;
     H.dev = D;
-    for (const BundlePanelDev& pd : panels) {
-      H.items.push_back(pd.nbundles * pd.tiles);
-      H.pack.push_back(pd.pack);
-    }
     out_devs.push_back(std::move(H));
   }
 }
@@ -465,7 +369,7 @@ LevelLayout plain_layout(const snfft_plan* plan, int k) {
 void upload_phases(snfft_plan* plan, int k) {
   const LevelLayout lay = plain_layout(plan, k);
   auto up = [&](const auto& v) { return plan->upload(v); };
-  build_phase_devs(plan->host.programs[k], lay, plan->level_dev[k].coef, up, plan->phase_dev[k]);
+  build_phase_devs(plan->host.programs[k], lay, up, plan->phase_dev[k]);
 }
 
 void upload_p1(snfft_plan* plan, int k) {
@@ -534,7 +438,8 @@ void run_phases(const std::vector<PhaseHost>& phases, const P1Dev& p1, int num_s
   for (int i = 1; i < np; ++i)
   {
       const PhaseHost& H = phases[inverse ? np - i : i];
-      CUDA_OK(launch_phase(H.dev, H.items.data(), H.pack.data(), xside, sside, groups, inverse, num_sms, stream));
+      CUDA_OK(launch_phase(H.dev, H.groups.data(), H.tiles.data(), H.pack.data(), xside, sside, groups, inverse,
+                           num_sms, stream));
     }
   if (inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, true, num_sms, stream));
 }
@@ -711,7 +616,7 @@ void build_shard_level(snfft_shard* sh, int k) {
     lay.block_stride = s_in;
     lay.lgroups_hint = host.fact[host.n] / host.fact[k];
     auto up = [&](const auto& v) { return shard_upload(sh, v); };
-    build_phase_devs(prog, lay, L.coef, up, SL.phases);
+    build_phase_devs(prog, lay, up, SL.phases);
     build_p1_dev(prog, lay, up, SL.p1);
   }
 }
@@ -1003,6 +908,58 @@ int snfft_yor(const snfft_plan* plan_, int irrep, const int32_t* perms_dev, int6
     YorTables& t = yor_tables_for(plan, irrep);
     CUDA_OK(launch_yor(plan->host.n, (int)s.dim, t.partner, t.diag, perms_dev, count, out_dev,
                        (cudaStream_t)stream));
+  });
+}
+
+int snfft_inverse_at(const snfft_plan* plan_, const double* fhat_dev, const int32_t* perms_dev, int64_t count,
+                     double* out_dev, void* stream) {
+  snfft_plan* plan = const_cast<snfft_plan*>(plan_);  // lazily cached generator / item tables
+  return guarded([&] {
+    require_device(plan);
+    if (count < 0) throw InvalidArg("count < 0");
+    if (count == 0) return;
+    if (!fhat_dev || !perms_dev || !out_dev) throw InvalidArg("null device buffer");
+    DeviceGuard guard(plan->device);
+    const int n = plan->host.n;
+    const auto& shapes = plan->host.levels[n].shapes;
+    // generator tables of every irrep first (yor_tables_for takes lazy_mu itself)
+    std::vector<YorTables> tabs;
+    if (n >= 2)
+      for (size_t i = 0; i < shapes.size(); ++i) tabs.push_back(yor_tables_for(plan, (int)i));
+    {
+      std::lock_guard<std::mutex> lock(plan->lazy_mu);
+      if (!plan->inv_at_items) {
+        // column tiles: the d x w tile of an irrep has to fit 96 KB of shared memory
+        std::vector<InvAtItem> items;
+        std::vector<InvAtIrrep> irreps;
+        size_t smem = 0;
+        for (size_t i = 0; i < shapes.size(); ++i) {
+          const int d = (int)shapes[i].dim;
+          int w = (int)std::min<int64_t>(d, std::max<int64_t>(1, 12288 / d));
+          const int nt = (d + w - 1) / w;
+          w = (d + nt - 1) / nt;
+          if ((size_t)d * w * sizeof(double) > 200 * 1024) throw std::runtime_error("irrep too large for the sampled inverse");
+          smem = std::max(smem, (size_t)d * w * sizeof(double));
+          for (int c0 = 0; c0 < d; c0 += w) items.push_back(InvAtItem{(int32_t)i, c0, std::min(w, d - c0), 0});
+          InvAtIrrep R{};
+          R.d = d;
+          R.off = shapes[i].off;
+          R.partner = n >= 2 ? tabs[i].partner : nullptr;
+          R.diag = n >= 2 ? tabs[i].diag : nullptr;
+          R.weight = (double)d / (double)plan->host.fact[n];
+          irreps.push_back(R);
+        }
+        plan->inv_at_irreps = plan->upload(irreps);
+        plan->inv_at_nitems = (int)items.size();
+        plan->inv_at_smem = smem;
+        plan->inv_at_items = plan->upload(items);
+      }
+    }
+    for (int64_t at = 0; at < count; at += 65535) {
+      const int64_t cnt = std::min<int64_t>(65535, count - at);
+      CUDA_OK(launch_inverse_at(n, plan->inv_at_items, plan->inv_at_nitems, plan->inv_at_irreps, plan->inv_at_smem,
+                                fhat_dev, perms_dev + at * n, cnt, out_dev + at, (cudaStream_t)stream));
+    }
   });
 }
 
@@ -1443,6 +1400,18 @@ int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t
   });
 }
 
+int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
+                 int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream) {
+  return guarded([&] {
+    if (!in_re_dev || !freq_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null device buffer");
+    if (inverse && !in_im_dev) throw InvalidArg("the adjoint transform needs the imaginary plane");
+    if (m < 1 || m > 9) throw InvalidArg("m must be in 1..9");
+    if (nfreq < 1 || count < 0) throw InvalidArg("bad shape");
+    CUDA_OK(launch_c3_dft(m, in_re_dev, in_im_dev, freq_dev, nfreq, count, out_re_dev, out_im_dev, inverse != 0,
+                          (cudaStream_t)stream));
+  });
+}
+
 int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev, int64_t count, int width,
                  void* stream) {
   return guarded([&] {
@@ -1453,7 +1422,7 @@ int snfft_gather(const double* src_dev, const int64_t* idx_dev, double* dst_dev,
 }
 
 int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes, int32_t* panels,
-                       int64_t* bundles, int64_t* rows, int32_t* blocks, int32_t* stage_first) {
+                       int64_t* groups, void* blob_fwd, void* blob_inv) {
   return guarded([&] {
     if (!plan || !sizes) throw InvalidArg("null argument");
     if (k < kPhaseMinLevel || k > plan->host.n) throw InvalidArg("row-group phases exist for levels 9..n");
@@ -1469,49 +1438,33 @@ int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes,
     };
     std::vector<PhaseHost> devs;
     const LevelLayout lay = plain_layout(plan, k);
-    build_phase_devs(prog, lay, prog.coef.data(), up, devs);
-    const BundleDev& D = devs[phase].dev;
-    int32_t nbundles = 0;
-    for (int p = 0; p < D.npanels; ++p) nbundles += D.panels[p].nbundles;
-    int64_t nrows = 0, nblocks = 0;
-    for (int b = 0; b < nbundles; ++b) {
-      nrows += D.bundles[b].nrows & 0xffffu;
-      nblocks += D.stage_first[D.bundles[b].stage_off + D.nstages * (kPhaseWarpsHost + 1) - 1];
-    }
+    build_phase_devs(prog, lay, up, devs);
+    const PhaseDev& D = devs[phase].dev;
+    int32_t ngroups = 0;
+    for (int p = 0; p < D.npanels; ++p) ngroups += D.panels[p].ngroups;
+    int64_t words = 0;
+    for (int g = 0; g < ngroups; ++g) words = std::max<int64_t>(words, (int64_t)D.groups[g].blob_off + D.groups[g].blob_len);
     sizes[0] = D.npanels;
-    sizes[1] = nbundles;
-    sizes[2] = (int32_t)nrows;
-    sizes[3] = (int32_t)nblocks;
-    sizes[4] = nbundles * D.nstages * (kPhaseWarpsHost + 1);
-    sizes[5] = D.cols_per_lane;
-    sizes[6] = D.nstages;
-    sizes[7] = D.max_rows;
-    sizes[8] = prog.panels[0].phases[phase].stage_lo;
-    sizes[9] = nphases;
+    sizes[1] = ngroups;
+    sizes[2] = (int32_t)words;
+    sizes[3] = D.max_rows;
+    sizes[4] = D.max_blob;
+    sizes[5] = D.nstages;
+    sizes[6] = prog.panels[0].phases[phase].stage_lo;
+    sizes[7] = nphases;
     for (int p = 0; p < D.npanels && panels; ++p) {
-      const BundlePanelDev& pd = D.panels[p];
-      const int32_t rec[5] = {pd.d, pd.tiles, pd.bundle_off, pd.nbundles, pd.pack};
+      const PhasePanelDev& pd = D.panels[p];
+      const int32_t rec[5] = {pd.d, pd.tiles, pd.grp_off, pd.ngroups, pd.pack};
       std::copy(rec, rec + 5, panels + 5 * p);
     }
-    for (int b = 0; b < nbundles && bundles; ++b) {
-      const Bundle& B = D.bundles[b];
-      bundles[4 * b] = B.row_off;
-      bundles[4 * b + 1] = B.blk_off;
-      bundles[4 * b + 2] = B.stage_off;
-      bundles[4 * b + 3] = B.nrows & 0xffffu;
-      for (uint32_t r = 0; r < (B.nrows & 0xffffu) && rows; ++r) {
-        rows[3 * (B.row_off + r)] = D.row_xoff[B.row_off + r];
-        rows[3 * (B.row_off + r) + 1] = D.row_dest[B.row_off + r];
-        rows[3 * (B.row_off + r) + 2] = r >= (B.nrows >> 16) ? 1 : 0;
-      }
+    for (int g = 0; g < ngroups && groups; ++g) {
+      groups[4 * g] = D.groups[g].blob_off;
+      groups[4 * g + 1] = D.groups[g].blob_len;
+      groups[4 * g + 2] = D.groups[g].nrows & 0xffffu;
+      groups[4 * g + 3] = D.groups[g].nrows >> 16;
     }
-    for (int64_t b = 0; b < nblocks && blocks; ++b) {
-      for (int a = 0; a < kMaxBlock; ++a) blocks[8 * b + a] = a < D.blocks_f[b].m ? D.blocks_f[b].loc[a] : -1;
-      blocks[8 * b + 5] = D.blocks_f[b].m;
-      blocks[8 * b + 6] = (int32_t)D.blocks_f[b].coef;
-      blocks[8 * b + 7] = (int32_t)D.blocks_i[b].coef;
-    }
-    for (int i = 0; i < sizes[4] && stage_first; ++i) stage_first[i] = (int32_t)D.stage_first[i];
+    if (blob_fwd) std::memcpy(blob_fwd, D.blob_f, (size_t)words * 16);
+    if (blob_inv) std::memcpy(blob_inv, D.blob_i, (size_t)words * 16);
   });
 }
 

@@ -42,46 +42,41 @@ struct Tile {
   int32_t cap;
 };
 
-// Row-group phase of a level (levels >= 9): see plan.hpp.  The groups of a panel are packed into
-// "bundles" (as many whole groups as fit the shared-memory tile of a CTA); a CTA loads the rows of
-// one bundle for a tile of 32 * cols_per_lane columns, runs the bundle's blocks stage by stage
-// (one barrier per stage, warps take blocks round-robin, lanes = columns) and stores the rows.
-struct alignas(16) BundleBlock {
-  uint16_t loc[kMaxBlock];  // rows of the block, as indices into the bundle's row list
-  uint8_t m;
-  uint8_t pad;
-  uint32_t coef;            // offset (doubles) of the m x m matrix in the level's coefficient pool
+// Row-group phase of a level (levels >= 9): see plan.hpp.  Every group of a panel comes with a
+// "program blob" that the host lays out once (capi.cu: build_phase_devs): the row table followed by
+// the group's blocks as a byte stream that a warp copies into shared memory and then interprets
+// for many column chunks - no pointer chasing and no table decoding in the inner loop.
+//   blob = u32 xoff[nrows], u32 dest[nrows] (padded to 16 bytes), then per block
+//          a 16-byte header {u16 byte offset of its m rows in the warp's tile [5]; u16 m; u32 0}
+//          followed by the m x m matrix (doubles, row-major out x in, padded to 16 bytes),
+//          terminated by a header with m = 0.
+// Rows that stay on the x side come first, rows finished in this phase last.
+struct alignas(16) U128 {
+  uint32_t x, y, z, w;
 };
-static_assert(sizeof(BundleBlock) == 16, "BundleBlock must be 16 bytes");
-struct Bundle {
-  uint32_t row_off;    // first row in BundleDev::row_xoff / row_dest
-  uint32_t blk_off;    // first block in BundleDev::blocks_*
-  uint32_t stage_off;  // stage_first[stage_off + s * 17 + w] .. [+ w + 1]: blocks of warp w in the s-th stage (relative)
-  uint32_t nrows;      // low 16 bits: rows; high 16 bits: rows that are NOT finished in this phase (they come first)
+struct PhaseGroupDev {
+  uint32_t blob_off;   // in 16-byte units, into PhaseDev::blob_f / blob_i
+  uint32_t blob_len;   // 16-byte units (row table + stream + terminator)
+  uint32_t nrows;      // low 16 bits: rows; high 16 bits: rows that are NOT finished in this phase
+  uint32_t reserved;
 };
-struct BundlePanelDev {
+struct PhasePanelDev {
   int32_t d;           // columns of the panel
-  int32_t tiles;       // ceil(d / (32 * cols_per_lane)); 1 when several lg members share the tile
-  int32_t bundle_off;  // first bundle in BundleDev::bundles
-  int32_t nbundles;
-  int64_t item_off;    // prefix sum of nbundles * tiles
-  int32_t pack;        // narrow panels: floor(32 * cols_per_lane / d) members of the lg loop side by side
+  int32_t tiles;       // ceil(d / 32); 1 when several lg members share the warp
+  int32_t grp_off;     // first group in PhaseDev::groups
+  int32_t ngroups;
+  int32_t pack;        // narrow panels (d <= 16): floor(32 / d) members of the lg loop side by side
   int32_t magic;       // ceil(65536 / d): (c * magic) >> 16 = c / d for c < 256
 };
-struct BundleDev {
-  const BundlePanelDev* panels;
-  const Bundle* bundles;
-  const uint32_t* row_xoff;     // per row: offset of its in-place slot in the x-side buffer
-  const uint32_t* row_dest;     // per row: offset of the finished row in the spectrum-side buffer
-  const BundleBlock* blocks_f;  // forward coefficients
-  const BundleBlock* blocks_i;  // inverse coefficients (same rows)
-  const uint32_t* stage_first;
-  const double* coef;
-  int64_t nitems;
+struct PhaseDev {
+  const PhasePanelDev* panels;
+  const PhaseGroupDev* groups;
+  const U128* blob_f;    // forward programs
+  const U128* blob_i;    // inverse programs (blocks in reverse order, transposed weighted matrices)
   int64_t in_stride, out_stride;  // group strides of the X-side and spectrum-side buffers
   int32_t npanels;
-  int32_t max_rows;       // rows of the largest bundle (shared-memory tile = max_rows x 32 * cols_per_lane)
-  int32_t cols_per_lane;  // 1, 2, 4 or 8
+  int32_t max_rows;       // rows of the largest group (tile of a warp = max_rows x 32 doubles)
+  int32_t max_blob;       // 16-byte units of the largest blob
   int32_t nstages;
 };
 
@@ -128,6 +123,18 @@ struct ShardPull {
   const int32_t* idx;             // device, m! entries
   int64_t nblocks, mfact;
   int32_t rank, world;
+};
+
+// Sampled inverse (kernels.cu: inverse_at_kernel): one item = columns [c0, c0 + w) of one irrep.
+struct InvAtItem {
+  int32_t irrep, c0, w, pad;
+};
+struct InvAtIrrep {
+  int32_t d, pad;
+  int64_t off;             // packed offset of f_hat(lambda)
+  const int32_t* partner;  // [(n-1)][d] generator tables (as for yor_kernel)
+  const double* diag;
+  double weight;           // d_lambda / n!
 };
 
 // Device-side barrier between ranks (kernels.cu: shard_barrier_kernel).  pads[r] = rank r's signal

@@ -20,6 +20,7 @@
 #include "gen_small.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -710,23 +711,19 @@ level8_kernel(L8Launch launch, const double* __restrict__ in, double* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// row-group phase kernel (levels >= 9).  One CTA = one (bundle of row groups, tile of 32 * CPL
-// columns): the rows of the bundle are staged into shared memory with cp.async (coalesced runs of
-// 256 bytes per warp and row), the bundle's blocks run stage by stage (warps take blocks
-// round-robin, lanes = columns, CPL columns per lane share one read of the block descriptor and of
-// its coefficients; one barrier per stage), and the rows go back in place or, when finished, to the
-// spectrum.  Narrow panels (column shards) put several members of the group loop side by side.
+// row-group phase kernel (levels >= 9).  One warp = one (row group, segment of its column chunks):
+// the warp copies the group's program blob (row table + block stream with inline coefficients,
+// laid out by the host) into its private shared memory once, then for every chunk of 32 columns
+// (lanes = columns; narrow panels put several members of the group loop side by side) stages the
+// group's rows with cp.async, interprets the stream on its lane-private column - one 16-byte
+// broadcast read per block header, the matrix from shared memory, no global table reads, no
+// barriers - and stores the rows back in place or, when finished, to the spectrum.
 // ---------------------------------------------------------------------------------------------
-// One persistent CTA of 16 warps per SM with TWO tiles in shared memory: the rows of the next unit
-// of work are in flight (cp.async) while the current tile runs its stages and is stored.  The
-// instruction budget is what bounds this kernel (the DFMAs are < 0.3 warp instructions per element),
-// so everything per block is shared by as many columns as shared memory allows (CPL up to 8: 256
-// columns per descriptor read), rows are addressed with 32-bit offsets off one 64-bit base, and the
-// rows of a bundle are sorted so that neither the load nor the store loop selects a buffer per row.
-constexpr int kPhaseWarps = 16;
 constexpr int kPhaseMaxPanels = 64;  // >= number of partitions of 11 (56)
 struct PhaseLaunch {
-  uint32_t work_off[kPhaseMaxPanels + 1];  // prefix sums of bundles * tiles * ceil(lgroups / pack) over the panels
+  uint32_t work_off[kPhaseMaxPanels + 1];  // prefix sums of groups * segments over the panels
+  uint32_t seg_len[kPhaseMaxPanels];       // chunks per segment of a panel
+  uint32_t nchunks[kPhaseMaxPanels];       // tiles * ceil(lgroups / pack) of a panel
 };
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -735,203 +732,196 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void cp_async8_s(unsigned smem_addr, const double* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
-
-// y[c][a] = sum_b cm[a][b] x[c][b] for CPL columns per lane with one read of the descriptor and of
-// the m x m matrix (16-byte loads; every matrix starts on a 16-byte boundary, the pool is padded)
-template <int M, int CPL>
-__device__ __forceinline__ void block_apply(const double* __restrict__ cmat, const BundleBlock& blk,
-                                            double* __restrict__ col) {
-  constexpr int W = 32 * CPL;
-  double cm[M * M + 1];
-  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(cmat);
-#pragma unroll
-  for (int i = 0; i < (M * M + 1) / 2; ++i) {
-    const double2 v = __ldg(c2 + i);
-    cm[2 * i] = v.x;
-    if (2 * i + 1 < M * M + 1) cm[2 * i + 1] = v.y;
-  }
-  double* row[M];
-#pragma unroll
-  for (int b = 0; b < M; ++b) row[b] = col + (int)blk.loc[b] * W;
-#pragma unroll
-  for (int cc = 0; cc < CPL; ++cc) {
-    double x[M], y[M];
-#pragma unroll
-    for (int b = 0; b < M; ++b) x[b] = row[b][cc * 32];
-#pragma unroll
-    for (int a = 0; a < M; ++a) {
-      double acc = cm[a * M] * x[0];
-#pragma unroll
-      for (int b = 1; b < M; ++b) acc = fma(cm[a * M + b], x[b], acc);
-      y[a] = acc;
-    }
-#pragma unroll
-    for (int a = 0; a < M; ++a) row[a][cc * 32] = y[a];
-  }
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 
-// a unit of work: one bundle, one tile of columns (or `pack` members of the group loop side by side)
-struct PhaseWork {
-  const uint32_t* xoff;   // per row: offset in the x-side buffer
-  const uint32_t* dest;   // per row >= nlow: offset in the spectrum-side buffer (indexed like xoff)
-  const BundleBlock* blocks;
-  const uint32_t* split;
-  int nrows, nlow;        // rows [0, nlow) stay on the x side, rows [nlow, nrows) are finished in this phase
-  int d, pack, tile, magic;
-  uint32_t lg0;
-};
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v));
+}
+__device__ __forceinline__ U128 lds_u128(unsigned addr) {
+  U128 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds_f64x2(unsigned addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 
-// CPL = columns per lane: a tile is [rows of the bundle][32 * CPL columns]
-template <bool INV, int CPL>
-__global__ void __launch_bounds__(kPhaseWarps * 32, 1)
-phase_kernel(BundleDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __restrict__ sside,
-             uint32_t lgroups) {
+// one block of the stream: y = C x on the m rows named by the header, in place in the lane's A
+// columns.  pc = shared-memory address of the header, col = shared-memory address of the lane's
+// first column; row r of the tile starts at r * 256 * A bytes, the lane's columns are 256 bytes apart.
+template <int M, int A>
+__device__ __forceinline__ void stream_block(unsigned pc, const U128 h, unsigned col) {
+  double cm[M * M + 1];
+#pragma unroll
+  for (int i = 0; i < (M * M + 1) / 2; ++i) {
+    double a, b;
+    lds_f64x2(pc + 16u + 16u * i, a, b);
+    cm[2 * i] = a;
+    if (2 * i + 1 < M * M + 1) cm[2 * i + 1] = b;
+  }
+  unsigned row[5];
+  row[0] = col + (h.x & 0xffffu) * A;
+  row[1] = col + (h.x >> 16) * A;
+  row[2] = col + (h.y & 0xffffu) * A;
+  row[3] = col + (h.y >> 16) * A;
+  row[4] = col + (h.z & 0xffffu) * A;
+  double x[A][M], y[A][M];
+#pragma unroll
+  for (int q = 0; q < A; ++q)
+#pragma unroll
+    for (int b = 0; b < M; ++b) x[q][b] = lds_f64(row[b] + 256u * q);
+#pragma unroll
+  for (int q = 0; q < A; ++q)
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double acc = cm[a * M] * x[q][0];
+#pragma unroll
+      for (int b = 1; b < M; ++b) acc = fma(cm[a * M + b], x[q][b], acc);
+      y[q][a] = acc;
+    }
+#pragma unroll
+  for (int q = 0; q < A; ++q)
+#pragma unroll
+    for (int a = 0; a < M; ++a) sts_f64(row[a] + 256u * q, y[q][a]);
+}
+
+// A = chunks of 32 columns a warp runs side by side (one read of every header and matrix for both)
+template <bool INV, int A>
+__global__ void __launch_bounds__(512, 1)
+phase_kernel(PhaseDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __restrict__ sside,
+             uint32_t lgroups, int warp_doubles) {
   extern __shared__ double sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int W = 32 * CPL;
-  const BundleBlock* __restrict__ all_blocks = INV ? P.blocks_i : P.blocks_f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // the warp's private shared memory: [tile: max_rows x 32 A doubles][blob: max_blob x 16 bytes]
+  double* tile = sm + (size_t)warp * warp_doubles;
+  const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile + lane);  // the lane's first column
+  const unsigned blob_s = (unsigned)__cvta_generic_to_shared(tile + P.max_rows * 32 * A);
+  const U128* __restrict__ blobs = INV ? P.blob_i : P.blob_f;
   const uint32_t nwork = Lp.work_off[P.npanels];
 
-  auto decode = [&](uint32_t w, PhaseWork& k) {
+  for (uint32_t w = blockIdx.x * nwarps + warp; w < nwork; w += gridDim.x * nwarps) {
     int lo = 0, hi = P.npanels - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (Lp.work_off[mid] <= w) lo = mid; else hi = mid - 1;
     }
-    const BundlePanelDev pan = P.panels[lo];
-    const uint32_t nlg = (lgroups + pan.pack - 1) / pan.pack;
+    const PhasePanelDev pan = P.panels[lo];
+    const uint32_t seg = Lp.seg_len[lo], nch = Lp.nchunks[lo];
+    const uint32_t nseg = (nch + seg - 1) / seg;
     const uint32_t rem = w - Lp.work_off[lo];
-    const uint32_t item = rem / nlg;  // the lg loop is the fastest index: CTAs that run together share tables
-    k.lg0 = rem - item * nlg;
-    const uint32_t bundle = item / (uint32_t)pan.tiles;
-    k.tile = (int)(item - bundle * (uint32_t)pan.tiles);
-    const Bundle B = P.bundles[pan.bundle_off + bundle];
-    k.xoff = P.row_xoff + B.row_off;
-    k.dest = P.row_dest + B.row_off;
-    k.blocks = all_blocks + B.blk_off;
-    k.split = P.stage_first + B.stage_off;
-    k.nrows = (int)(B.nrows & 0xffffu);
-    k.nlow = (int)(B.nrows >> 16);
-    k.d = pan.d;
-    k.pack = pan.pack;
-    k.magic = pan.magic;
-  };
-  // lane -> CPL (member of the lg loop, column) pairs of a unit of work, as 32-bit element offsets
-  // relative to the buffers advanced to the first member; 0xffffffff = no column
-  auto columns = [&](const PhaseWork& k, uint32_t (&xo)[CPL], uint32_t (&so)[CPL]) {
-#pragma unroll
-    for (int cc = 0; cc < CPL; ++cc) {
-      const int c = lane + 32 * cc;
-      if (k.pack > 1) {
-        const int sub = (c * k.magic) >> 16;  // c / d for c < 256 (magic = ceil(65536 / d))
-        const int cg = c - sub * k.d;
-        const bool ok = sub < k.pack && k.lg0 * (uint32_t)k.pack + sub < lgroups;
-        xo[cc] = ok ? (uint32_t)sub * (uint32_t)P.in_stride + cg : 0xffffffffu;
-        so[cc] = ok ? (uint32_t)sub * (uint32_t)P.out_stride + cg : 0xffffffffu;
-      } else {
-        const int cg = k.tile * W + c;
-        xo[cc] = so[cc] = cg < k.d ? (uint32_t)cg : 0xffffffffu;
-      }
-    }
-  };
-  // all rows of the bundle in flight at once: global -> shared tile, no registers
-  auto issue_loads = [&](const PhaseWork& k, double* tile) {
-    uint32_t xo[CPL], so[CPL];
-    columns(k, xo, so);
-    const int64_t first = (int64_t)k.lg0 * k.pack;
-    const double* xb = xside + first * P.in_stride;
-    const double* sb = sside + first * P.out_stride;
-    const unsigned t0 = (unsigned)__cvta_generic_to_shared(tile + lane);
-    const int nx = INV ? k.nlow : k.nrows;  // rows read from the x side
-#pragma unroll 2
-    for (int r = warp; r < nx; r += kPhaseWarps) {
-      const uint32_t off = __ldg(k.xoff + r);
-#pragma unroll
-      for (int cc = 0; cc < CPL; ++cc)
-        if (xo[cc] != 0xffffffffu) cp_async8_s(t0 + (unsigned)(r * W + cc * 32) * 8u, xb + (off + xo[cc]));
-    }
-    if (INV) {
-      const int rs = k.nlow + ((warp - k.nlow) & (kPhaseWarps - 1));  // keep the round-robin over warps
-#pragma unroll 2
-      for (int r = rs; r < k.nrows; r += kPhaseWarps) {
-        const uint32_t off = __ldg(k.dest + r);
-#pragma unroll
-        for (int cc = 0; cc < CPL; ++cc)
-          if (so[cc] != 0xffffffffu) cp_async8_s(t0 + (unsigned)(r * W + cc * 32) * 8u, sb + (off + so[cc]));
-      }
-    }
+    const uint32_t g = rem / nseg, sg = rem - g * nseg;  // consecutive warps share a group (and its blob in L2)
+    const PhaseGroupDev G = P.groups[pan.grp_off + g];
+    const int nrows = (int)(G.nrows & 0xffffu), nlow = (int)(G.nrows >> 16);
+    // ---- the group's program: global -> the warp's shared memory, once per unit of work ---------
+    __syncwarp();  // the previous unit's stream is no longer read
+    const U128* __restrict__ gblob = blobs + G.blob_off;
+    for (uint32_t i = lane; i < G.blob_len; i += 32) cp_async16_s(blob_s + i * 16u, gblob + i);
     cp_async_commit();
-  };
-
-  const int tile_elems = P.max_rows * W;
-  PhaseWork cur, nxt;
-  uint32_t w = blockIdx.x;
-  if (w >= nwork) return;
-  decode(w, cur);
-  issue_loads(cur, sm);
-  int buf = 0;
-  while (true) {
-    const uint32_t wn = w + gridDim.x;
-    const bool more = wn < nwork;
-    if (more) {
-      decode(wn, nxt);
-      issue_loads(nxt, sm + (buf ^ 1) * tile_elems);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+    // the row table stays in registers, two rows per lane (groups have <= 64 rows), and is handed
+    // out with shuffles: no shared-memory read sits in front of the asynchronous copies
+    const uint32_t* __restrict__ gtab = reinterpret_cast<const uint32_t*>(gblob);
+    const uint32_t xoff0 = lane < nrows ? __ldg(gtab + lane) : 0u;
+    const uint32_t xoff1 = lane + 32 < nrows ? __ldg(gtab + lane + 32) : 0u;
+    const uint32_t dst0 = lane < nrows ? __ldg(gtab + nrows + lane) : 0u;
+    const uint32_t dst1 = lane + 32 < nrows ? __ldg(gtab + nrows + lane + 32) : 0u;
+    const unsigned stream = blob_s + 16u * (unsigned)((2 * nrows + 3) >> 2);
+    // lane -> (member of the lg loop, column)
+    int sub = 0, cg = lane;
+    if (pan.pack > 1) {
+      sub = (lane * pan.magic) >> 16;
+      cg = lane - sub * pan.d;
     }
-    __syncthreads();
-    double* col = sm + buf * tile_elems + lane;
-    for (int st = 0; st < P.nstages; ++st) {
-      const int s = INV ? P.nstages - 1 - st : st;
-      const int b0 = (int)cur.split[s * (kPhaseWarps + 1) + warp], b1 = (int)cur.split[s * (kPhaseWarps + 1) + warp + 1];
-      // the next descriptor is fetched while the current block runs
-      BundleBlock cb{};
-      if (b0 < b1) cb = cur.blocks[b0];
-      for (int bi = b0; bi < b1; ++bi) {
-        BundleBlock nb{};
-        if (bi + 1 < b1) nb = cur.blocks[bi + 1];
-        const double* cmat = P.coef + cb.coef;
-        switch (cb.m) {
-          case 2: block_apply<2, CPL>(cmat, cb, col); break;
-          case 3: block_apply<3, CPL>(cmat, cb, col); break;
-          case 4: block_apply<4, CPL>(cmat, cb, col); break;
-          default: block_apply<5, CPL>(cmat, cb, col); break;
-        }
-        cb = nb;
-      }
-      __syncthreads();
-    }
-    {
-      uint32_t xo[CPL], so[CPL];
-      columns(cur, xo, so);
-      const int64_t first = (int64_t)cur.lg0 * cur.pack;
-      double* xb = xside + first * P.in_stride;
-      double* sb = sside + first * P.out_stride;
-      const int nx = INV ? cur.nrows : cur.nlow;  // rows written to the x side
-#pragma unroll 2
-      for (int r = warp; r < nx; r += kPhaseWarps) {
-        const uint32_t off = __ldg(cur.xoff + r);
+    const uint32_t ntl = (uint32_t)pan.tiles;
+    const uint32_t c_end = min(nch, (sg + 1) * seg);
+    for (uint32_t ch0 = sg * seg; ch0 < c_end; ch0 += A) {
+      uintptr_t xb[A], sb[A];
+      bool ok[A];
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc)
-          if (xo[cc] != 0xffffffffu) xb[off + xo[cc]] = col[r * W + cc * 32];
+      for (int q = 0; q < A; ++q) {
+        // the tile index is the fastest one: neighbouring tiles of a row share 32-byte sectors, and
+        // they meet in L2 when one warp runs them back to back
+        const uint32_t ch = ch0 + q;
+        const uint32_t lgi = ch / ntl, tl = ch - lgi * ntl;
+        int64_t lg;
+        int c;
+        if (pan.pack > 1) {
+          lg = (int64_t)lgi * pan.pack + sub;
+          ok[q] = ch < c_end && sub < pan.pack && lg < (int64_t)lgroups;
+          c = cg;
+        } else {
+          lg = lgi;
+          c = (int)tl * 32 + lane;
+          ok[q] = ch < c_end && c < pan.d;
+        }
+        xb[q] = reinterpret_cast<uintptr_t>(xside + lg * P.in_stride + c);
+        sb[q] = reinterpret_cast<uintptr_t>(sside + lg * P.out_stride + c);
       }
+      // ---- rows: global -> lane-private shared columns, all in flight at once ---------------------
+      auto load_rows = [&](int r0, int r1, uint32_t tab, const uintptr_t (&base)[A]) {
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          const uint32_t off = __shfl_sync(0xffffffffu, tab, r & 31);
+#pragma unroll
+          for (int q = 0; q < A; ++q)
+            if (ok[q])
+              cp_async8_s(tile_s + (unsigned)r * (256u * A) + 256u * q,
+                          reinterpret_cast<const double*>(base[q] + (uint64_t)off * 8u));
+        }
+      };
+      const int nx = INV ? nlow : nrows;
+      load_rows(0, min(nx, 32), xoff0, xb);
+      load_rows(32, nx, xoff1, xb);
+      if (INV) {
+        load_rows(nlow, min(nrows, 32), dst0, sb);
+        load_rows(max(nlow, 32), nrows, dst1, sb);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();  // a lane only reads the rows it copied itself ...
+      __syncwarp();        // ... but the blob (first chunk) was copied by all lanes
+      // ---- the stream: the next header is fetched before the current block runs -----------------
+      unsigned pc = stream;
+      U128 h = lds_u128(pc);
+      while (true) {
+        const uint32_t m = h.z >> 16;
+        if (m == 0) break;
+        const unsigned next = pc + 16u + 16u * ((m * m + 1) >> 1);
+        const U128 hn = lds_u128(next);
+        switch (m) {
+          case 2: stream_block<2, A>(pc, h, tile_s); break;
+          case 3: stream_block<3, A>(pc, h, tile_s); break;
+          case 4: stream_block<4, A>(pc, h, tile_s); break;
+          default: stream_block<5, A>(pc, h, tile_s); break;
+        }
+        pc = next;
+        h = hn;
+      }
+      // ---- rows back: in place, or to the spectrum when finished ----------------------------------
+      auto store_rows = [&](int r0, int r1, uint32_t tab, const uintptr_t (&base)[A]) {
+#pragma unroll 4
+        for (int r = r0; r < r1; ++r) {
+          const uint32_t off = __shfl_sync(0xffffffffu, tab, r & 31);
+#pragma unroll
+          for (int q = 0; q < A; ++q)
+            if (ok[q])
+              *reinterpret_cast<double*>(base[q] + (uint64_t)off * 8u) =
+                  lds_f64(tile_s + (unsigned)r * (256u * A) + 256u * q);
+        }
+      };
+      const int nxs = INV ? nrows : nlow;
+      store_rows(0, min(nxs, 32), xoff0, xb);
+      store_rows(32, nxs, xoff1, xb);
       if (!INV) {
-        const int rs = cur.nlow + ((warp - cur.nlow) & (kPhaseWarps - 1));
-#pragma unroll 2
-        for (int r = rs; r < cur.nrows; r += kPhaseWarps) {
-          const uint32_t off = __ldg(cur.dest + r);
-#pragma unroll
-          for (int cc = 0; cc < CPL; ++cc)
-            if (so[cc] != 0xffffffffu) sb[off + so[cc]] = col[r * W + cc * 32];
-        }
+        store_rows(nlow, min(nrows, 32), dst0, sb);
+        store_rows(max(nlow, 32), nrows, dst1, sb);
       }
     }
-    if (!more) break;
-    __syncthreads();  // this tile is free for the loads of the work after next
-    cur = nxt;
-    w = wn;
-    buf ^= 1;
   }
 }
 
@@ -1213,6 +1203,147 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stage 1 of the wreath-product transform (wreath.py:43-58, :123-143): the
+// character sums over the orientations, F_i(sigma) = sum_o f(sigma, o) chi_i(o), are values of the
+// DFT of f(sigma, .) over C_3^m at the frequencies of the alpha-orbit.  One CTA = one sigma: the
+// 3^m orientation values (17.5 KB for the 2x2 cube) sit in shared memory as re / im planes, m
+// radix-3 passes run in place, and only the N needed frequencies are written.  INV: the adjoint -
+// the N values are scattered onto the frequency grid and the conjugate DFT gives all 3^m values.
+// ---------------------------------------------------------------------------------------------
+template <bool INV>
+__global__ void __launch_bounds__(kThreads)
+c3_dft_kernel(int m, int size, const double* __restrict__ in_re, const double* __restrict__ in_im,
+              const int32_t* __restrict__ freq, int nfreq, double* __restrict__ out_re,
+              double* __restrict__ out_im) {
+  extern __shared__ double grid[];
+  double* re = grid;
+  double* im = grid + size;
+  const int64_t sig = blockIdx.x;
+  if (!INV) {
+    for (int e = threadIdx.x; e < size; e += kThreads) {
+      re[e] = in_re[sig * size + e];
+      im[e] = 0.0;
+    }
+  } else {
+    for (int e = threadIdx.x; e < size; e += kThreads) re[e] = im[e] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nfreq; i += kThreads) {
+      re[freq[i]] = in_re[sig * nfreq + i];
+      im[freq[i]] = in_im[sig * nfreq + i];
+    }
+  }
+  __syncthreads();
+  const double h = 0.8660254037844386467637231707529;  // sqrt(3) / 2
+  const double sgn = INV ? -1.0 : 1.0;                  // forward: omega^{+k o}; adjoint: omega^{-k o}
+  int stride = 1;
+  for (int a = 0; a < m; ++a, stride *= 3) {
+    for (int t = threadIdx.x; t < size / 3; t += kThreads) {
+      const int hi = t / stride, lo = t - hi * stride;
+      const int base = hi * 3 * stride + lo;
+      const double x0r = re[base], x0i = im[base];
+      const double x1r = re[base + stride], x1i = im[base + stride];
+      const double x2r = re[base + 2 * stride], x2i = im[base + 2 * stride];
+      const double sr = x1r + x2r, si = x1i + x2i;          // x1 + x2
+      const double dr = (x1r - x2r) * h * sgn, di = (x1i - x2i) * h * sgn;  // (x1 - x2) * (+-sqrt(3)/2)
+      re[base] = x0r + sr;
+      im[base] = x0i + si;
+      // X_1 = x0 - (x1 + x2)/2 + i (x1 - x2) sqrt(3)/2 ; X_2 = x0 - (x1 + x2)/2 - i (x1 - x2) sqrt(3)/2
+      re[base + stride] = x0r - 0.5 * sr - di;
+      im[base + stride] = x0i - 0.5 * si + dr;
+      re[base + 2 * stride] = x0r - 0.5 * sr + di;
+      im[base + 2 * stride] = x0i - 0.5 * si - dr;
+    }
+    __syncthreads();
+  }
+  if (!INV) {
+    for (int i = threadIdx.x; i < nfreq; i += kThreads) {
+      out_re[sig * nfreq + i] = re[freq[i]];
+      out_im[sig * nfreq + i] = im[freq[i]];
+    }
+  } else {
+    for (int e = threadIdx.x; e < size; e += kThreads) {
+      out_re[sig * size + e] = re[e];
+      out_im[sig * size + e] = im[e];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampled inverse (tile/par_inv_ft.py:27-45, compute_policy.py:66-88): f(sigma_j) for a batch of
+// permutations straight from the packed spectrum,
+//   f(sigma) = (1/n!) sum_lambda d_lambda tr(rho_lambda(sigma)^T f_hat(lambda)),
+// without materialising rho: rho(sigma)^T = rho(t_1) ... rho(t_L) applied to f_hat(lambda) from the
+// left as 2-sparse row rotations (columns are independent), then the trace.  One CTA = one
+// (sigma_j, irrep, tile of columns): the d x w tile sits in shared memory, the word is applied
+// generator by generator, the partial trace is added to out[j].  All irreps in ONE launch.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+inverse_at_kernel(int n, const InvAtItem* __restrict__ items, const InvAtIrrep* __restrict__ irreps,
+                  const double* __restrict__ fhat, const int32_t* __restrict__ perms,
+                  double* __restrict__ out) {
+  extern __shared__ double tile[];
+  __shared__ int word[kMaxN * kMaxN];
+  __shared__ int wlen;
+  __shared__ double partial[kThreads / 32];
+  const InvAtItem it = items[blockIdx.x];
+  const InvAtIrrep R = irreps[it.irrep];
+  const int64_t pid = blockIdx.y;
+  const int d = R.d, w = it.w;
+  if (threadIdx.x == 0) {
+    // the same bubble-sort word as yor_kernel (yor.py:19-38)
+    int p[kMaxN];
+    for (int i = 0; i < n; ++i) p[i] = perms[pid * n + i];
+    int len = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = n - 1; j > i; --j)
+        if (p[j] < p[j - 1]) {
+          const int tmp = p[j];
+          p[j] = p[j - 1];
+          p[j - 1] = tmp;
+          word[len++] = j;
+        }
+    wlen = len;
+  }
+  const double* __restrict__ F = fhat + R.off + it.c0;
+  for (int e = threadIdx.x; e < d * w; e += kThreads) {
+    const int r = e / w, c = e - r * w;
+    tile[e] = F[(int64_t)r * d + c];
+  }
+  __syncthreads();
+  // yor_kernel builds rho(sigma) = G_L ... G_1 (G_t = generator of the t-th recorded swap, all
+  // symmetric), so rho(sigma)^T f_hat = G_1 (G_2 ... (G_L f_hat)): the last recorded swap first
+  for (int t = wlen - 1; t >= 0; --t) {
+    const int j = word[t];
+    const int32_t* __restrict__ pr = R.partner + (int64_t)(j - 1) * d;
+    const double* __restrict__ dg = R.diag + (int64_t)(j - 1) * d;
+    for (int e = threadIdx.x; e < d * w; e += kThreads) {
+      const int r = e / w, c = e - r * w;
+      const int q = pr[r];
+      const double a = dg[r];
+      if (q < 0) {
+        tile[e] = a * tile[e];
+      } else if (q > r) {
+        const double b = sqrt(1 - a * a);
+        const double x = tile[r * w + c], y = tile[q * w + c];
+        tile[r * w + c] = a * x + b * y;
+        tile[q * w + c] = b * x - a * y;
+      }
+    }
+    __syncthreads();
+  }
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < w; c += kThreads) acc += tile[(it.c0 + c) * w + c];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) sum += partial[i];
+    atomicAdd(out + pid, R.weight * sum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fp64 GEMM on the DMMA pipe: C[M,N] = A[M,K] B[K,N], row-major.  Each warp owns a 16x16 tile
 // of C as 2x2 mma.m8n8k4 fragments; a CTA of 8 warps covers 64x32... (simple, oracle-sized).
 // ---------------------------------------------------------------------------------------------
@@ -1224,6 +1355,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16;
 
+// generic shapes (any M, N, K; edges handled per element): synchronous shared-memory tiles
 __global__ void __launch_bounds__(256)
 dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
              int M, int N, int K) {
@@ -1274,6 +1406,95 @@ dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double*
         if (c < N) C[(int64_t)r * N + c] = acc[i][j][0];
         if (c + 1 < N) C[(int64_t)r * N + c + 1] = acc[i][j][1];
       }
+    }
+}
+
+// Large aligned shapes (K a multiple of 16, N even, 16-byte aligned operands): 128 x 128 x 16 tiles,
+// three stages of 16-byte cp.async (zero fill past the edges), 8 warps of 64 x 32 (8 x 4 fragments
+// of mma.m8n8k4: 32 DMMAs per 12 shared-memory loads).  Tile strides 20 / 132 doubles keep both
+// fragment loads conflict-free per half warp.
+constexpr int kG2BM = 128, kG2BN = 128, kG2BK = 16, kG2Stages = 3;
+constexpr int kG2SA = kG2BK + 4, kG2SB = kG2BN + 4;  // padded strides (doubles)
+constexpr int kG2StageDoubles = kG2BM * kG2SA + kG2BK * kG2SB;
+
+__device__ __forceinline__ void cp_async16_zfill(unsigned smem_addr, const void* gsrc, bool valid) {
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+dgemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                  int M, int N, int K) {
+  extern __shared__ double gsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kG2BM, n0 = blockIdx.x * kG2BN;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;  // 2 warps along M x 4 along N
+  const int grp = lane >> 2, tig = lane & 3;
+  const unsigned smem0 = (unsigned)__cvta_generic_to_shared(gsm);
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto stage_in = [&](int stage, int k0) {
+    const unsigned sa = smem0 + (unsigned)(stage * kG2StageDoubles) * 8u;
+    const unsigned sb = sa + (unsigned)(kG2BM * kG2SA) * 8u;
+    // A tile: 128 rows x 16 doubles = 8 chunks of 16 bytes per row
+#pragma unroll
+    for (int q = 0; q < (kG2BM * kG2BK / 2) / 256; ++q) {
+      const int e = threadIdx.x + q * 256;
+      const int r = e >> 3, c = (e & 7) * 2;
+      const bool ok = m0 + r < M;  // K is a multiple of 16: no edge along k
+      const double* src = A + (int64_t)(ok ? m0 + r : 0) * K + k0 + c;
+      cp_async16_zfill(sa + (unsigned)(r * kG2SA + c) * 8u, src, ok);
+    }
+    // B tile: 16 rows x 128 doubles = 64 chunks per row
+#pragma unroll
+    for (int q = 0; q < (kG2BK * kG2BN / 2) / 256; ++q) {
+      const int e = threadIdx.x + q * 256;
+      const int r = e >> 6, c = (e & 63) * 2;
+      const bool ok = n0 + c < N;  // N is even: a chunk is inside or outside as a whole
+      const double* src = B + (int64_t)(k0 + r) * N + (ok ? n0 + c : 0);
+      cp_async16_zfill(sb + (unsigned)(r * kG2SB + c) * 8u, src, ok);
+    }
+    cp_async_commit();
+  };
+
+  const int nk = K / kG2BK;
+#pragma unroll
+  for (int s = 0; s < kG2Stages - 1; ++s) {
+    if (s < nk) stage_in(s, s * kG2BK); else cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<kG2Stages - 2>();  // tile kt has landed (for this thread's copies) ...
+    __syncthreads();                 // ... and for everybody's; the stage read last iteration is free
+    if (kt + kG2Stages - 1 < nk) stage_in((kt + kG2Stages - 1) % kG2Stages, (kt + kG2Stages - 1) * kG2BK);
+    else cp_async_commit();
+    const double* sA = gsm + (kt % kG2Stages) * kG2StageDoubles;
+    const double* sB = sA + kG2BM * kG2SA;
+#pragma unroll
+    for (int kk = 0; kk < kG2BK; kk += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = sA[(wm + i * 8 + grp) * kG2SA + kk + tig];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[(kk + tig) * kG2SB + wn + j * 8 + grp];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm + i * 8 + grp;
+      const int c = n0 + wn + j * 8 + 2 * tig;
+      if (r < M && c < N)  // N even, c even: the pair is inside or outside as a whole
+        *reinterpret_cast<double2*>(C + (int64_t)r * N + c) = make_double2(acc[i][j][0], acc[i][j][1]);
     }
 }
 
@@ -1370,8 +1591,8 @@ Facts make_facts() {
 
 namespace {
 template <class K>
-cudaError_t allow_big_smem(K kernel) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+cudaError_t allow_big_smem(K kernel, int kb = 227) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
 }
 }  // namespace
 
@@ -1379,14 +1600,15 @@ cudaError_t prepare_kernels() {
   cudaError_t e;
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(dgemm_pipe_kernel, 200)) != cudaSuccess) return e;
+  // (kernels with static shared memory of their own: dynamic + static must stay <= 227 KB)
+  if ((e = allow_big_smem(inverse_at_kernel, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<false>, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<true>, 200)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 1>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<true, 1>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 2>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<true, 2>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<false, 4>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<true, 4>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<false, 8>)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(phase_kernel<true, 8>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
@@ -1468,39 +1690,65 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
   return cudaGetLastError();
 }
 
-template <int CPL>
-static cudaError_t launch_phase_cpl(const BundleDev& P, const PhaseLaunch& Lp, double* xside, double* sside,
-                                    int64_t lgroups, bool inverse, int num_sms, cudaStream_t stream) {
-  const size_t smem = 2 * (size_t)P.max_rows * 32 * CPL * sizeof(double);
-  int64_t grid = Lp.work_off[P.npanels];
-  if (grid > num_sms) grid = num_sms;  // persistent: one CTA per SM, units of work grid-strided
-  LaunchScope scope(inverse ? kKindPhaseInv : kKindPhaseFwd, stream);
-  if (inverse)
-    phase_kernel<true, CPL><<<(unsigned)grid, kPhaseWarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups);
-  else
-    phase_kernel<false, CPL><<<(unsigned)grid, kPhaseWarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_phase(const BundleDev& P, const int32_t* panel_items, const int32_t* panel_pack,
-                         double* xside, double* sside, int64_t lgroups, bool inverse, int num_sms,
-                         cudaStream_t stream) {
-  if (lgroups <= 0 || P.nitems <= 0) return cudaSuccess;
+cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const int32_t* panel_tiles,
+                         const int32_t* panel_pack, double* xside, double* sside, int64_t lgroups,
+                         bool inverse, int num_sms, cudaStream_t stream) {
+  if (lgroups <= 0 || P.npanels <= 0) return cudaSuccess;
   if (P.npanels > kPhaseMaxPanels || lgroups > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // shared memory of a warp: its tile (A chunks of 32 columns side by side) plus the largest program
+  // blob; as many warps per CTA (one CTA per SM) as fit, at most 16.  Two chunks per warp halve the
+  // per-block overhead and double the independent work of a warp: measured faster even when only
+  // 7 warps fit (48-row groups; S_12 forward + inverse 45.0 -> 41.7 ms).  SNFFT_PHASE_A overrides.
+  int A = 1;
+  {
+    const size_t two = ((size_t)P.max_rows * 64 + P.max_blob * 2) * sizeof(double);
+    if ((226 * 1024) / two >= 6) A = 2;
+    if (const char* env = std::getenv("SNFFT_PHASE_A")) A = std::atoi(env) == 2 ? 2 : 1;
+  }
+  const int warp_doubles = P.max_rows * 32 * A + P.max_blob * 2;
+  int nwarps = (int)((226 * 1024) / ((size_t)warp_doubles * sizeof(double)));
+  if (nwarps > 16) nwarps = 16;
+  if (nwarps < 1) return cudaErrorInvalidValue;
+  // units of work: (group, segment of its chunks); segments long enough to amortise the blob copy,
+  // short enough to give every warp of the machine several units
   PhaseLaunch Lp;
+  int64_t total_chunks = 0;
+  for (int p = 0; p < P.npanels; ++p) {
+    const int64_t nlg = (lgroups + panel_pack[p] - 1) / panel_pack[p];
+    Lp.nchunks[p] = (uint32_t)(panel_tiles[p] * nlg);  // chunks of 32 columns
+    total_chunks += (int64_t)panel_groups[p] * Lp.nchunks[p];
+  }
+  const int64_t warps_total = (int64_t)num_sms * nwarps;
+  int64_t seg = total_chunks / (warps_total * 6);
+  if (seg < 4) seg = 4;
+  if (seg > 64) seg = 64;
+  seg = (seg + A - 1) / A * A;  // a warp runs A chunks at a time
   int64_t at = 0;
   for (int p = 0; p < P.npanels; ++p) {
     Lp.work_off[p] = (uint32_t)at;
-    at += (int64_t)panel_items[p] * ((lgroups + panel_pack[p] - 1) / panel_pack[p]);
+    Lp.seg_len[p] = (uint32_t)seg;
+    at += (int64_t)panel_groups[p] * ((Lp.nchunks[p] + seg - 1) / seg);
     if (at > 0x7fffffffLL) return cudaErrorInvalidValue;
   }
   for (int p = P.npanels; p <= kPhaseMaxPanels; ++p) Lp.work_off[p] = (uint32_t)at;
-  switch (P.cols_per_lane) {
-    case 8: return launch_phase_cpl<8>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
-    case 4: return launch_phase_cpl<4>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
-    case 2: return launch_phase_cpl<2>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
-    default: return launch_phase_cpl<1>(P, Lp, xside, sside, lgroups, inverse, num_sms, stream);
+  for (int p = P.npanels; p < kPhaseMaxPanels; ++p) Lp.seg_len[p] = 1, Lp.nchunks[p] = 0;
+  if (at == 0) return cudaSuccess;
+  int64_t grid = (at + nwarps - 1) / nwarps;
+  if (grid > num_sms) grid = num_sms;  // persistent: one CTA per SM, units of work grid-strided
+  const size_t smem = (size_t)nwarps * warp_doubles * sizeof(double);
+  LaunchScope scope(inverse ? kKindPhaseInv : kKindPhaseFwd, stream);
+  if (inverse) {
+    if (A == 2)
+      phase_kernel<true, 2><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
+    else
+      phase_kernel<true, 1><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
+  } else {
+    if (A == 2)
+      phase_kernel<false, 2><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
+    else
+      phase_kernel<false, 1><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
   }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
@@ -1601,6 +1849,34 @@ cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
   return cudaGetLastError();
 }
 
+cudaError_t launch_inverse_at(int n, const InvAtItem* items, int nitems, const InvAtIrrep* irreps, size_t smem_bytes,
+                              const double* fhat, const int32_t* perms, int64_t count, double* out,
+                              cudaStream_t stream) {
+  if (count <= 0 || nitems <= 0) return cudaSuccess;
+  if (count > 65535) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)count * sizeof(double), stream);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)nitems, (unsigned)count);
+  LaunchScope scope(kKindYor, stream);
+  inverse_at_kernel<<<grid, kThreads, smem_bytes, stream>>>(n, items, irreps, fhat, perms, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
+                          int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  if (m < 1 || m > 9 || count > 0x7fffffffLL) return cudaErrorInvalidValue;
+  int size = 1;
+  for (int a = 0; a < m; ++a) size *= 3;
+  const size_t smem = 2 * (size_t)size * sizeof(double);
+  LaunchScope scope(kKindOther, stream);
+  if (inverse)
+    c3_dft_kernel<true><<<(unsigned)count, kThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+  else
+    c3_dft_kernel<false><<<(unsigned)count, kThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,
                           cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
@@ -1628,7 +1904,7 @@ cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, c
 }
 
 cudaError_t launch_shard_barrier(const ShardBarrier& Bq, cudaStream_t stream) {
-  LaunchScope scope(kKindExchange, stream);
+  LaunchScope scope(kKindBarrier, stream);
   shard_barrier_kernel<<<1, 32, 0, stream>>>(Bq);
   return cudaGetLastError();
 }
@@ -1636,8 +1912,16 @@ cudaError_t launch_shard_barrier(const ShardBarrier& Bq, cudaStream_t stream) {
 cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K,
                          cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
   LaunchScope scope(kKindDgemm, stream);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+                         reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+  if (aligned && K > 0 && K % kG2BK == 0 && N % 2 == 0 && N >= 64 && (int64_t)M * N >= 128 * 128) {
+    dim3 grid((N + kG2BN - 1) / kG2BN, (M + kG2BM - 1) / kG2BM);
+    const size_t smem = (size_t)kG2Stages * kG2StageDoubles * sizeof(double);
+    dgemm_pipe_kernel<<<grid, 256, smem, stream>>>(A, B, C, M, N, K);
+    return cudaGetLastError();
+  }
+  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
   dgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K);
   return cudaGetLastError();
 }

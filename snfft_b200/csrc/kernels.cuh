@@ -15,7 +15,7 @@ extern std::atomic<bool> g_force_table_driven;  // tests: route level 8 through 
 // Optional per-launch timing (bench.py): when enabled every launch is bracketed by CUDA events on
 // its own stream; timing_read() synchronises the recorded events and returns the totals per kind.
 enum KernelKind { kKindFusedFwd = 0, kKindFusedInv, kKindLevel8Fwd, kKindLevel8Inv, kKindLevelTable,
-                  kKindP1, kKindP0, kKindPhaseFwd, kKindPhaseInv, kKindExchange, kKindReorder,
+                  kKindP1, kKindP0, kKindPhaseFwd, kKindPhaseInv, kKindExchange, kKindBarrier, kKindReorder,
                   kKindYor, kKindDgemm, kKindOther, kNumKinds };
 void timing_enable(bool on);
 void timing_read(double* ms_by_kind, int64_t* launches_by_kind);  // also resets the totals
@@ -29,10 +29,10 @@ cudaError_t launch_level(const LevelDev& L, const Tile* tiles_dev, int ntiles, s
 
 // One row-group phase of a level: xside holds the in-place rows (input of the level, clobbered by
 // the forward direction; output of the level in the inverse direction), sside the finished rows.
-// panel_items[p] = bundles * tiles of panel p, panel_pack[p] = its pack (host copies of the device tables).
-cudaError_t launch_phase(const BundleDev& P, const int32_t* panel_items, const int32_t* panel_pack,
-                         double* xside, double* sside, int64_t lgroups, bool inverse, int num_sms,
-                         cudaStream_t stream);
+// panel_groups / panel_tiles / panel_pack: host copies of the per-panel fields of the device tables.
+cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const int32_t* panel_tiles,
+                         const int32_t* panel_pack, double* xside, double* sside, int64_t lgroups,
+                         bool inverse, int num_sms, cudaStream_t stream);
 
 // Stages 1..4 of a large level as in-place generated programs plus the pass that moves the rows
 // finished after stage 4 to / from the spectrum-side buffer.
@@ -53,9 +53,19 @@ cudaError_t launch_build_lex_table(int n, uint32_t* table, cudaStream_t stream);
 cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
                        const int32_t* perms, int64_t count, double* out, cudaStream_t stream);
 
+// f(sigma_j) for `count` permutations from one packed spectrum (all irreps in one launch); out is zeroed first.
+cudaError_t launch_inverse_at(int n, const InvAtItem* items, int nitems, const InvAtIrrep* irreps, size_t smem_bytes,
+                              const double* fhat, const int32_t* perms, int64_t count, double* out,
+                              cudaStream_t stream);
+
 // C[M,N] = A[M,K] * B[K,N], fp64 row-major, on the DMMA pipe (mma.sync.m8n8k4.f64).
 cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int N, int K,
                          cudaStream_t stream);
+
+// DFT over C_3^m of `count` rows: forward real [count][3^m] -> complex at the nfreq listed frequency
+// indices; inverse (adjoint): complex [count][nfreq] -> complex [count][3^m].
+cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
+                          int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream);
 
 // dst[e][0..width) = src[idx[e]][0..width)
 cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,

@@ -128,7 +128,7 @@ struct HostPlan {
 void build_host_plan(int n, HostPlan& plan);
 
 constexpr int kPhaseMinLevel = 9;   // levels >= 9 run as row-group phases
-constexpr int kPhaseMaxRows = 448;  // rows of a group (shared-memory tile of a CTA: rows x 32 columns <= 112 KB)
+constexpr int kPhaseMaxRows = 64;   // rows of a group (the phase kernel keeps the row table in two registers per lane)
 
 // Stage ranges of the phases of level k >= 9: [1..4] first, then the ranges given by their last
 // stages.  Default: 5..8 and 9..k-1 (groups of <= 48 rows, so that the tiles of the phase kernel can

@@ -148,20 +148,19 @@ def inverse_at(fhat, n, perms):
     """f(sigma_j) for a list of permutation tuples -- the sampled inverse that the reference's
     consumers run per state (tile/par_inv_ft.py:27-45, compute_policy.py:66-88):
     f(sigma) = (1/n!) sum_lambda d_lambda sum(f_hat(lambda) o rho_lambda(sigma)).
-    rho_lambda(sigma_j) comes from the device YOR kernel, one batched call per irrep."""
+    One device launch for all irreps and all states (``snfft_inverse_at``)."""
     import torch
     plan = get_plan(n, _DEVICE)
-    parts, dims, _ = plan.layout()
+    parts, dims, offs = plan.layout()
     by_part = {(k.partition if hasattr(k, 'partition') else tuple(k)): v for k, v in fhat.items()}
     dev = f'cuda:{_DEVICE}'
+    packed = np.empty(plan.size, dtype=np.float64)
+    for p, d, o in zip(parts, dims, offs):
+        packed[o:o + d * d] = np.asarray(by_part[p], dtype=np.float64).reshape(d * d)
     tuples = [tuple(p.tup_rep) if hasattr(p, 'tup_rep') else tuple(p) for p in perms]
     pt = torch.tensor([t + tuple(range(len(t) + 1, n + 1)) for t in tuples], dtype=torch.int32,
                       device=dev).reshape(-1, n)
-    out = torch.zeros(len(tuples), dtype=torch.float64, device=dev)
-    for i, (p, d) in enumerate(zip(parts, dims)):
-        mat = torch.as_tensor(np.asarray(by_part[p], dtype=np.float64), device=dev)
-        out += d * (plan.yor(i, pt) * mat).sum(dim=(1, 2))
-    return (out / math.factorial(n)).cpu().numpy()
+    return plan.inverse_at(torch.from_numpy(packed).to(dev), pt).cpu().numpy()
 
 
 def cube2_inv_fft_part(irrep_dict, fourier_mat, coset_reps, cyclic_irrep_func, cyc_tup, perm_tup):

@@ -117,19 +117,17 @@ class Plan:
     def export_phase(self, k: int, phase: int):
         """Host copy of the device tables of one row-group phase of level k >= 9 (see
         ``snfft_export_phase``): what ``phase_kernel`` executes, for CPU tests."""
-        sizes = np.zeros(10, dtype=np.int32)
-        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), None, None, None, None, None))
-        npan, nbun, nrows, nblk, nsf = (int(v) for v in sizes[:5])
+        sizes = np.zeros(8, dtype=np.int32)
+        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), None, None, None, None))
+        npan, ngrp, words = (int(v) for v in sizes[:3])
         panels = np.zeros((npan, 5), dtype=np.int32)
-        bundles = np.zeros((nbun, 4), dtype=np.int64)
-        rows = np.zeros((nrows, 3), dtype=np.int64)
-        blocks = np.zeros((nblk, 8), dtype=np.int32)
-        stage_first = np.zeros(nsf, dtype=np.int32)
-        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), N.ptr(panels), N.ptr(bundles),
-                                         N.ptr(rows), N.ptr(blocks), N.ptr(stage_first)))
-        return dict(panels=panels, bundles=bundles, rows=rows, blocks=blocks, stage_first=stage_first,
-                    cols_per_lane=int(sizes[5]), nstages=int(sizes[6]), max_rows=int(sizes[7]),
-                    stage_lo=int(sizes[8]), nphases=int(sizes[9]))
+        groups = np.zeros((ngrp, 4), dtype=np.int64)
+        blob_f = np.zeros(words * 16, dtype=np.uint8)
+        blob_i = np.zeros(words * 16, dtype=np.uint8)
+        N.check(N.lib.snfft_export_phase(self._h, k, phase, N.ptr(sizes), N.ptr(panels), N.ptr(groups),
+                                         N.ptr(blob_f), N.ptr(blob_i)))
+        return dict(panels=panels, groups=groups, blob_fwd=blob_f, blob_inv=blob_i, max_rows=int(sizes[3]),
+                    max_blob=int(sizes[4]), nstages=int(sizes[5]), stage_lo=int(sizes[6]), nphases=int(sizes[7]))
 
     # ------------------------------------------------------------------ device transforms
     def _check(self, t, name, last=None):
@@ -210,6 +208,23 @@ class Plan:
         with torch.cuda.device(self.device):
             N.check(N.lib.snfft_yor(self._h, irrep, N.ptr(perms), perms.shape[0], N.ptr(out),
                                     self._stream()))
+        return out
+
+    def inverse_at(self, fhat, perms):
+        """f(sigma_j) for int32 CUDA tensor perms [count, n] from ONE packed spectrum fhat [n!]
+        (``snfft_inverse_at``: all irreps in one launch)."""
+        import torch
+        self._check(fhat, "fhat", self.size)
+        if fhat.numel() != self.size:
+            raise ValueError("inverse_at takes a single packed spectrum [n!]")
+        if perms.dtype != torch.int32 or not perms.is_cuda or not perms.is_contiguous():
+            raise TypeError("perms must be a contiguous int32 CUDA tensor")
+        if perms.dim() != 2 or perms.shape[1] != self.n:
+            raise ValueError(f"perms must have shape [count, {self.n}]")
+        out = torch.empty(perms.shape[0], dtype=torch.float64, device=perms.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.snfft_inverse_at(self._h, N.ptr(fhat), N.ptr(perms), perms.shape[0], N.ptr(out),
+                                           self._stream()))
         return out
 
     def dft_direct(self, f):
@@ -299,7 +314,7 @@ def launch_count() -> int:
 
 
 KERNEL_KINDS = ("fused_fwd", "fused_inv", "level8_fwd", "level8_inv", "level_table", "p1", "p0", "phase_fwd",
-                "phase_inv", "exchange", "reorder", "yor", "dgemm", "other")
+                "phase_inv", "exchange", "barrier", "reorder", "yor", "dgemm", "other")
 
 
 def timing_enable(on: bool) -> None:

@@ -192,17 +192,83 @@ def _lex_ranks(perms):
     return rank
 
 
+def orientation_mode(oris, n):
+    """How the orientation axis is laid out: 'zero_sum' = the tuples of {0,1,2}^n with sum = 0 mod 3
+    in itertools.product order (utils.py:206-209: the index is the base-3 number of the first n-1
+    letters), 'full' = all 3^n tuples in product order, None = anything else."""
+    oris = np.asarray(oris, dtype=np.int64).reshape(-1, n)
+    pw = 3 ** np.arange(n - 1, -1, -1)
+    if len(oris) == 3 ** n and np.array_equal(oris @ pw, np.arange(3 ** n)):
+        return 'full'
+    if len(oris) == 3 ** (n - 1) and np.array_equal(oris[:, :n - 1] @ pw[1:], np.arange(3 ** (n - 1))) \
+            and not (oris.sum(axis=1) % 3).any():
+        return 'zero_sum'
+    return None
+
+
+def dft_frequencies(alpha, reps, mode):
+    """Index of chi_i on the frequency grid of the C_3^m DFT (``snfft_c3_dft``) for every coset
+    representative t_i.  chi_i(o) = omega^{sum_q e_i(q) o_q} with e_i(t_i(p)) = k for p in the k-th
+    alpha-segment (wreath.py:34-58, :123-143); on the zero-sum subgroup o_n = -(o_1 + .. + o_{n-1}),
+    so chi_i is the character (e_i(q) - e_i(n)) mod 3 of C_3^{n-1}."""
+    n = sum(alpha)
+    T = np.array(reps, dtype=np.int64)
+    seg = np.repeat(np.arange(3), alpha)                      # segment of position p
+    e = np.empty_like(T)
+    np.put_along_axis(e, T - 1, np.broadcast_to(seg, T.shape), axis=1)   # e[i, t_i(p) - 1] = seg(p)
+    if mode == 'full':
+        return (e @ (3 ** np.arange(n - 1, -1, -1))).astype(np.int32)
+    k = (e[:, :n - 1] - e[:, n - 1:]) % 3
+    return (k @ (3 ** np.arange(n - 2, -1, -1))).astype(np.int32)
+
+
+_ALPHA_TABLES = {}
+
+
+def _alpha_tables(alpha, device):
+    """Tables that depend on alpha only (shared by all `parts`): coset representatives and the
+    gather index sigma = t_i h t_j^-1 for every (i, j, h)."""
+    import torch
+    key = (tuple(alpha), device)
+    if key not in _ALPHA_TABLES:
+        reps = young_coset_reps(alpha)
+        N_ = len(reps)
+        T = np.array(reps, dtype=np.int64)
+        H = np.array([p.tup_rep for p in young_subgroup_perm(alpha)], dtype=np.int64)   # [nH, n]
+        Tinv = np.argsort(T, axis=1) + 1
+        hT = H[:, Tinv - 1]                                           # h(t_j^-1(p)) : [nH, N, n]
+        idx = np.empty((N_, N_, len(H)), dtype=np.int64)
+        for i in range(N_):
+            sig = T[i][hT - 1]                                        # t_i(h(t_j^-1(p)))
+            idx[i] = _lex_ranks(sig).T * N_ + i
+        flat = idx.reshape(-1)
+        inv = np.empty_like(flat)
+        inv[flat] = np.arange(flat.size)
+        dev = f'cuda:{device}'
+        _ALPHA_TABLES[key] = dict(reps=reps, T=T, nH=len(H), idx=torch.from_numpy(flat).to(dev),
+                                  inv_idx=torch.from_numpy(inv).to(dev))
+        if len(_ALPHA_TABLES) > 4:                                   # the big ones hold 360 MB of indices
+            _ALPHA_TABLES.pop(next(iter(_ALPHA_TABLES)))
+    return _ALPHA_TABLES[key]
+
+
 class WreathPlan:
     """Fourier transform of functions on C_3^n x S_n (orientations restricted to ``oris``) at one
     irrep (alpha, parts).  f is a float64 CUDA tensor [n!, len(oris)]: sigma in ``sn(n)`` order
-    (slow axis), orientation index (fast axis)."""
+    (slow axis), orientation index (fast axis).
+
+    Stage 1 (character sums over the orientations) is a radix-3 DFT over C_3^m in shared memory
+    (``snfft_c3_dft``: one pass over f) whenever the orientation axis is the standard one
+    (``orientation_mode``); an arbitrary orientation list falls back to the dense character GEMM.
+    Stage 2 (sum over the Young subgroup per coset pair) is one gather plus one DMMA GEMM."""
 
     def __init__(self, alpha, parts, oris=None, device: int = 0):
         import torch
         self.alpha, self.parts, self.device = tuple(alpha), tuple(tuple(p) for p in parts), device
         self.n = n = sum(alpha)
         dev = f'cuda:{device}'
-        self.reps = young_coset_reps(self.alpha)
+        tabs = _alpha_tables(self.alpha, device)
+        self.reps = tabs['reps']
         self.N = len(self.reps)
         self.block = wreath_dim(self.parts)
         self.D = self.N * self.block
@@ -210,17 +276,22 @@ class WreathPlan:
             oris = [t for t in itertools.product((0, 1, 2), repeat=n) if sum(t) % 3 == 0]   # utils.py:206-209
         self.oris = np.array(oris, dtype=np.int64).reshape(-1, n)
         self.order = math.factorial(n) * len(self.oris)
-        # characters chi_i(o) (wreath.py:34-58): o o t_i summed over the alpha-segments
-        T = np.array(self.reps, dtype=np.int64)                       # [N, n]
-        a, b = self.alpha[0], self.alpha[0] + self.alpha[1]
-        og = self.oris[:, T - 1]                                      # [n_ori, N, n]
-        expo = (og[:, :, a:b].sum(-1) + 2 * og[:, :, b:].sum(-1)) % 3
-        omega = np.exp(2j * np.pi * np.arange(3) / 3.)
-        X = omega[expo]                                               # [n_ori, N]
-        self.Xre = torch.from_numpy(np.ascontiguousarray(X.real)).to(dev)
-        self.Xim = torch.from_numpy(np.ascontiguousarray(X.imag)).to(dev)
-        self.XreT = self.Xre.t().contiguous()
-        self.XimT = self.Xim.t().contiguous()
+        self.mode = orientation_mode(self.oris, n)
+        T = tabs['T']
+        if self.mode is not None:
+            self.dft_m = n if self.mode == 'full' else n - 1
+            self.freq = torch.from_numpy(dft_frequencies(self.alpha, self.reps, self.mode)).to(dev)
+        else:
+            # characters chi_i(o) (wreath.py:34-58): o o t_i summed over the alpha-segments
+            a, b = self.alpha[0], self.alpha[0] + self.alpha[1]
+            og = self.oris[:, T - 1]                                      # [n_ori, N, n]
+            expo = (og[:, :, a:b].sum(-1) + 2 * og[:, :, b:].sum(-1)) % 3
+            omega = np.exp(2j * np.pi * np.arange(3) / 3.)
+            X = omega[expo]                                               # [n_ori, N]
+            self.Xre = torch.from_numpy(np.ascontiguousarray(X.real)).to(dev)
+            self.Xim = torch.from_numpy(np.ascontiguousarray(X.imag)).to(dev)
+            self.XreT = self.Xre.t().contiguous()
+            self.XimT = self.Xim.t().contiguous()
         # R[h] = kron_k rho_{parts_k}(h_k), h in itertools.product order (wreath.py:191-224)
         R = None
         for ak, pk in zip(self.alpha, self.parts):
@@ -235,21 +306,11 @@ class WreathPlan:
                 R = torch.einsum('xab,ycd->xyacbd', R, mats).reshape(
                     R.shape[0] * mats.shape[0], R.shape[1] * mats.shape[1], R.shape[2] * mats.shape[2])
         self.nH = R.shape[0]
+        assert self.nH == tabs['nH']
         self.R = R.reshape(self.nH, self.block * self.block).contiguous()
         self.RT = self.R.t().contiguous()
         # sigma = t_i h t_j^-1 for every (i, j, h): one gather index into F[sigma][i]
-        H = np.array([p.tup_rep for p in young_subgroup_perm(self.alpha)], dtype=np.int64)   # [nH, n]
-        Tinv = np.argsort(T, axis=1) + 1
-        idx = np.empty((self.N, self.N, self.nH), dtype=np.int64)
-        for i in range(self.N):
-            hT = H[:, Tinv - 1]                                       # h(t_j^-1(p)) : [nH, N, n]
-            sig = T[i][hT - 1]                                        # t_i(h(t_j^-1(p)))
-            idx[i] = _lex_ranks(sig).T * self.N + i
-        flat = idx.reshape(-1)
-        inv = np.empty_like(flat)
-        inv[flat] = np.arange(flat.size)
-        self.idx = torch.from_numpy(flat).to(dev)
-        self.inv_idx = torch.from_numpy(inv).to(dev)
+        self.idx, self.inv_idx = tabs['idx'], tabs['inv_idx']
 
     # -- thin wrappers over the C ABI
     def _gemm(self, a, b):
@@ -268,6 +329,24 @@ class WreathPlan:
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out
 
+    def _dft(self, re, im, inverse):
+        """``snfft_c3_dft``: forward real [n!, 3^m] -> (re, im) [n!, N]; inverse the adjoint."""
+        import torch
+        count = re.shape[0]
+        width = 3 ** self.dft_m if inverse else self.N
+        out_re = torch.empty((count, width), dtype=torch.float64, device=re.device)
+        out_im = torch.empty((count, width), dtype=torch.float64, device=re.device)
+        N.check(N.lib.snfft_c3_dft(self.dft_m, N.ptr(re), N.ptr(im) if im is not None else None, N.ptr(self.freq),
+                                   self.N, count, N.ptr(out_re), N.ptr(out_im), int(inverse),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out_re, out_im
+
+    def character_sums(self, f):
+        """Stage 1: (re, im) of F_i(sigma) = sum_o f(sigma, o) chi_i(o), each [n!, N]."""
+        if self.mode is not None:
+            return self._dft(f, None, False)
+        return self._gemm(f, self.Xre), self._gemm(f, self.Xim)
+
     def forward(self, f):
         """complex128 [D, D] = sum_g f(g) rho(g)."""
         import torch
@@ -276,8 +355,7 @@ class WreathPlan:
         f = f.contiguous()
         with torch.cuda.device(self.device):
             planes = []
-            for X in (self.Xre, self.Xim):
-                F = self._gemm(f, X)                                  # [n!, N]  character sums
+            for F in self.character_sums(f):                          # [n!, N]
                 G = self._gather(F.reshape(-1), self.idx)             # [N*N*nH] regrouped by cosets
                 planes.append(self._gemm(G.reshape(self.N * self.N, self.nH), self.R))
         out = torch.complex(planes[0], planes[1]).reshape(self.N, self.N, self.block, self.block)
@@ -294,9 +372,51 @@ class WreathPlan:
             for plane in (B.real.contiguous(), B.imag.contiguous()):
                 e = self._gemm(plane, self.RT)                        # [N*N, nH]
                 E.append(self._gather(e.reshape(-1), self.inv_idx).reshape(math.factorial(self.n), self.N))
-            re = self._gemm(E[0], self.XreT) + self._gemm(E[1], self.XimT)
-            im = self._gemm(E[1], self.XreT) - self._gemm(E[0], self.XimT)
+            if self.mode is not None:
+                re, im = self._dft(E[0], E[1], True)
+            else:
+                re = self._gemm(E[0], self.XreT) + self._gemm(E[1], self.XimT)
+                im = self._gemm(E[1], self.XreT) - self._gemm(E[0], self.XimT)
         return torch.complex(re, im) * (self.D / self.order)
+
+    def inverse_at(self, fhat, elements):
+        """D tr(rho(g)^H f_hat) / |G| at chosen group elements [(orientation tuple, permutation
+        tuple), ...] (cube_ift.py:56-67 per state, the consumer-facing form of
+        compute_policy.py:66-88).  Only the rows sigma = t_i h t_j^-1 that g touches are formed:
+        for every j the coset i of sigma t_j is known, so the trace runs over N blocks, not N^2."""
+        import torch
+        dev = fhat.device
+        b, N_ = self.block, self.N
+        T = np.array(self.reps, dtype=np.int64)
+        index = {tuple(t): i for i, t in enumerate(self.reps)}
+        seg = np.repeat(np.arange(3), self.alpha)
+        a_, b_ = self.alpha[0], self.alpha[0] + self.alpha[1]
+        blocks = fhat.reshape(N_, b, N_, b).permute(0, 2, 1, 3)       # [i, j, b, b]
+        omega = np.exp(2j * np.pi * np.arange(3) / 3.)
+        Hlist = [p.tup_rep for p in young_subgroup_perm(self.alpha)]
+        hindex = {h: q for q, h in enumerate(Hlist)}
+        out = []
+        Rm = self.R.reshape(self.nH, b, b)
+        for ori, sigma in elements:
+            sig = np.array(sigma, dtype=np.int64)
+            ii, hh = [], []
+            for j in range(N_):
+                st = sig[T[j] - 1]                                    # sigma t_j
+                rep = np.concatenate([np.sort(st[:a_]), np.sort(st[a_:b_]), np.sort(st[b_:])])
+                i = index[tuple(int(v) for v in rep)]
+                h = tuple(int(v) for v in (np.argsort(T[i]) + 1)[st - 1])   # t_i^-1 sigma t_j
+                ii.append(i)
+                hh.append(hindex[h])
+            o = np.array(ori, dtype=np.int64)
+            expo = (o[T[ii][:, a_:b_] - 1].sum(-1) + 2 * o[T[ii][:, b_:] - 1].sum(-1)) % 3
+            chi = torch.from_numpy(omega[expo]).to(dev)               # D(o)_ii
+            it = torch.tensor(ii, device=dev)
+            jt = torch.arange(N_, device=dev)
+            blk = blocks[it, jt]                                      # f_hat block (i(j), j): [N, b, b]
+            rho = Rm[torch.tensor(hh, device=dev)]                    # rho_parts(h_j): [N, b, b] real
+            val = (chi.conj()[:, None, None] * rho * blk).sum()
+            out.append(val * (self.D / self.order))
+        return torch.stack(out)
 
 
 def wreath_forward(f, alpha, parts, oris=None, device: int = 0):

@@ -86,6 +86,31 @@ def test_yor_random_homomorphism_n7():
         assert np.allclose(yor(fd, g) @ yor(fd, h), yor(fd, g * h))
 
 
+@pytest.mark.parametrize('n', [2, 4, 5, 8, 9])
+def test_sampled_inverse_against_the_oracle(n):
+    """snfft_inverse_at (all irreps, all states in one launch) against the oracle's restatement of
+    tile/par_inv_ft.py:27-45 on a RANDOM spectrum (not the transform of a function: nothing of the
+    device forward path enters the expectation)."""
+    import torch
+    import snfft_oracle as O
+    from snfft_b200 import get_plan
+    rng = np.random.default_rng(40 + n)
+    plan = get_plan(n)
+    parts, dims, offs = plan.layout()
+    fhat = {p: rng.standard_normal((d, d)) for p, d in zip(parts, dims)}
+    if n <= 5:
+        perms = list(O.sn(n))
+    else:
+        perms = [tuple(int(v) + 1 for v in rng.permutation(n)) for _ in range(6)] + [tuple(range(1, n + 1))]
+    got = sfft.inverse_at(fhat, n, perms)
+    if n <= 5:
+        want = O.inverse_direct(fhat, n)
+    else:
+        nf = math.factorial(n)
+        want = np.array([sum(d * (fhat[p] * O.yor(p, g)).sum() for p, d in zip(parts, dims)) / nf for g in perms])
+    assert np.abs(got - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
+
+
 def test_sampled_inverse_and_file_job(tmp_path):
     # tile/par_inv_ft.py:27-45 per state, summed over irreps; s8fft.do_all_ffts from a text table
     from snfft_b200 import io

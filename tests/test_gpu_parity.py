@@ -244,6 +244,67 @@ def test_direct_sum_gemm_matches_oracle(golden_small, n):
     assert per_irrep_err(plan, got[1:], fast) < TOL
 
 
+def test_direct_sum_gemm_s8_against_reference_golden(golden_s8):
+    """snfft_dft_direct at n = 8 (the [8!, 8!] matrix of all rho_lambda(sigma) is 13 GB, built on the
+    device) against the reference's own fourier_transform2 of functions 0, 511, 1023 of the seed-8
+    batch (tests/golden/reference_s8.npz)."""
+    n = 8
+    plan = get_plan(n)
+    f = np.random.default_rng(8).standard_normal((1024, math.factorial(n)))
+    rows = golden_s8['rows']
+    try:
+        got = plan.dft_direct(dev(np.ascontiguousarray(f[rows]))).cpu().numpy()
+    finally:
+        plan.dft_release()
+    assert per_irrep_err(plan, got, golden_s8['direct_8']) < TOL
+    assert plan.device_bytes() < 1 << 30          # the matrix is gone again
+
+
+def test_misaligned_buffers_are_rejected():
+    """The fused kernel stages its input with 16-byte cp.async: a float64 view at an odd element
+    offset must be refused with SNFFT_ERR_INVALID instead of faulting."""
+    from snfft_b200 import _native as N
+    n = 7
+    plan = get_plan(n)
+    nf = math.factorial(n)
+    base = torch.zeros(2 * nf + 2, dtype=torch.float64, device='cuda')
+    out, work = torch.empty(nf, dtype=torch.float64, device='cuda'), torch.empty(nf, dtype=torch.float64, device='cuda')
+    odd = base[1:1 + nf]
+    assert odd.data_ptr() % 16 == 8
+    with pytest.raises(N.SnfftError):
+        plan.forward(odd, 'coset', out=out, work=work)
+    with pytest.raises(N.SnfftError):
+        plan.inverse(odd, 'coset', out=out, work=work)
+    torch.cuda.synchronize()                      # no sticky error: the context is still usable
+    assert plan.forward(base[:nf], 'coset', out=out, work=work).abs().max().item() == 0.0
+
+
+def test_largest_irreps_columns_against_oracle_s10_s12():
+    """n = 10 and 12: columns of the LARGEST irreps (d = 768 / d = 7700, 5632, 5775: the 48-row
+    groups of the phase kernel) for a sparse-support input against columns of rho_lambda(sigma)
+    built by the oracle's restatement of yor.py - not by the device's own yor kernel."""
+    import parity_tools as PT
+    for n in (10, 12):
+        plan = get_plan(n)
+        parts, dims, offs = plan.layout()
+        perms, coefs = PT.sparse_support(n, count=3, seed=n)
+        x = torch.zeros(math.factorial(n), dtype=torch.float64, device='cuda')
+        for p_, c_ in zip(perms, coefs):
+            x[PT.O.coset_index(p_)] += float(c_)
+        spec = plan.forward(x, 'coset')
+        del x
+
+        def get_columns(i, cols):
+            d = dims[i]
+            return spec[offs[i]:offs[i] + d * d].reshape(d, d)[:, cols].cpu().numpy()
+        irreps = PT.pick_irreps(parts, dims, big=4, small=4)
+        worst, checked = PT.check_columns(get_columns, parts, dims, perms, coefs, irreps)
+        assert worst < TOL, checked
+        assert max(d for _, d, _, _ in checked) == max(dims)
+        del spec
+        torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize('n', [9, 10])
 def test_large_n_properties(n):
     """n = 9, 10: the reference cannot run; the oracle port runs n = 9 only on a sample.  Check

@@ -82,7 +82,9 @@ def test_plancherel_over_all_irreps_of_c3_wr_s4():
                                          ((8, 0, 0), ((7, 1), (), ())),             # cube_ft.py:127-128, D = 7
                                          ((1, 2, 5), ((1,), (1, 1), (3, 2))),       # test_wreath.py:77-78, D = 840
                                          ((2, 3, 3), ((2,), (1, 1, 1), (1, 1, 1))), # cube_irrep.py:179-180, D = 560
-                                         ((4, 2, 2), ((4,), (2,), (2,)))])          # gen_sparse.py:135-137, D = 420
+                                         ((4, 2, 2), ((4,), (2,), (2,))),           # gen_sparse.py:135-137, D = 420
+                                         ((2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))),  # test_wreath.py:53-54, D = 1120
+                                         ((0, 4, 4), ((), (2, 2), (3, 1)))])        # cube_sp_irrep.py:79-80, D = 420
 def test_cube_irreps_sparse_support(alpha, parts):
     """BASELINE configs[3]: the 2x2 cube group (3^7 * 8! elements).  f supported on a few group
     elements: f_hat must equal sum_j c_j rho(g_j) built by the oracle."""
@@ -128,3 +130,44 @@ def sparse_rho(wp, alpha, parts, o, g):
             blk = np.kron(blk, m)
         mat[i * b:(i + 1) * b, j * b:(j + 1) * b] = scal[i] * blk
     return mat
+
+
+def test_plancherel_over_all_270_cube_irreps():
+    """sum over the 270 irreps of the 2x2 cube group of D ||f_hat||_F^2 = |G| ||f||^2
+    (utils.cube2_irreps: 15 alphas up to cyclic shift x the partition triples), sum D^2 = |G|."""
+    from snfft_b200.utils import cube2_irreps
+    irreps = list(cube2_irreps())
+    assert len(irreps) == 270
+    f = torch.randn((40320, 2187), dtype=torch.float64, device='cuda',
+                    generator=torch.Generator(device='cuda').manual_seed(38))
+    total, dims = 0.0, 0
+    for alpha, parts in sorted(irreps, key=lambda ap: ap[0]):       # one alpha after the other: cached tables
+        wp = WreathPlan(alpha, parts)
+        fh = wp.forward(f)
+        total += wp.D * (fh.abs() ** 2).sum().item()
+        dims += wp.D ** 2
+        del fh, wp
+    assert dims == 88179840
+    want = 88179840 * (f ** 2).sum().item()
+    assert abs(total - want) / want < 1e-11
+
+
+@pytest.mark.parametrize('ci', range(3))
+def test_sampled_wreath_inverse_against_oracle(ci):
+    """WreathPlan.inverse_at (d tr(rho(g)^H f_hat) / |G| per state, cube_ift.py:56-67) on a RANDOM
+    complex f_hat against the oracle's direct evaluation, C3 wr S5."""
+    alpha, parts = CASES[ci]
+    n = sum(alpha)
+    oris = W.orientations(n)
+    wp = WreathPlan(alpha, parts)
+    rng = np.random.default_rng(300 + ci)
+    fhat = rng.standard_normal((wp.D, wp.D)) + 1j * rng.standard_normal((wp.D, wp.D))
+    want = W.wreath_inverse_direct(alpha, parts, fhat, oris, math.factorial(n) * len(oris))   # [n!, n_ori]
+    group = list(itertools.permutations(range(1, n + 1)))
+    picks = [(int(rng.integers(len(group))), int(rng.integers(len(oris)))) for _ in range(12)]
+    got = wp.inverse_at(torch.from_numpy(fhat).cuda(), [(oris[q], group[s]) for s, q in picks]).cpu().numpy()
+    ref = np.array([want[s, q] for s, q in picks])
+    assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    # and the dense device inverse agrees with the sampled one on the cube-sized path too
+    dense = wp.inverse(torch.from_numpy(fhat).cuda()).cpu().numpy()
+    assert np.abs(dense - want).max() < 1e-10 * max(1.0, np.abs(want).max())

@@ -123,3 +123,25 @@ def test_coset_major_order_is_a_bijection():
     # (2,4,1,5,3) <-> (i5,i4,i3,i2) = (3,4,1,2)
     flat = (3 - 1) * 24 + (4 - 1) * 6 + (1 - 1) * 2 + (2 - 1) * 1
     assert O.sn(5)[O.coset_major_to_lex(5)[flat]] == (2, 4, 1, 5, 3)
+
+
+def test_sparse_generator_forms_match_the_dense_ones():
+    """The helpers that let the checker reach n = 12 (single columns of rho_lambda(sigma), the
+    coset-major index of a permutation) against the pinned dense functions at small n."""
+    for n in (3, 4, 5, 6):
+        c2l = O.coset_major_to_lex(n)
+        group = O.sn(n)
+        for t in range(0, len(c2l), max(1, len(c2l) // 97)):
+            assert O.coset_index(group[c2l[t]]) == t
+    rng = np.random.default_rng(0)
+    for p in [(3, 2, 1), (4, 1, 1), (2, 2, 2), (5, 1)]:
+        for k in range(1, 6):
+            diag, partner, off = O.yor_trans_sparse(p, k)
+            dense = np.diag(diag)
+            rows = np.nonzero(partner >= 0)[0]
+            dense[rows, partner[rows]] = off[rows]
+            assert np.array_equal(dense, O.yor_trans(p, k))
+        for _ in range(5):
+            tup = tuple(int(v) + 1 for v in rng.permutation(6))
+            cols = [0, len(O.tableaux(p)) - 1, len(O.tableaux(p)) // 2]
+            assert np.allclose(O.yor_columns(p, tup, cols), O.yor(p, tup)[:, cols], atol=1e-14, rtol=0)

@@ -210,12 +210,11 @@ def test_reorder_tile_factorisation():
 def interpret_level_by_phases(plan, k, x, inverse=False):
     """Level k >= 9 the way the device runs it: stages 1..4 in place on the X side (export_panel
     blocks; on the device these are the generated programs plus the finished-row move), then every
-    row-group phase from the exported BUNDLE tables (what phase_kernel executes): per bundle load
-    its rows, run the blocks stage by stage, store rows in place or - when finished - to the
+    row-group phase from the exported program blobs (what phase_kernel executes): per group load
+    its rows, interpret the block stream, store rows in place or - when finished - to the
     spectrum.  x: [k, (k-1)!] forward, [k!] inverse."""
     parts, dims, offs = plan.layout(k - 1)
     kf = math.factorial(k)
-    coef = plan.export_coef(k)
     nphases = plan.export_phase(k, 1)['nphases']
     phases = [plan.export_phase(k, ph) for ph in range(1, nphases)]
     xs = np.zeros(kf) if inverse else x.reshape(-1).copy()
@@ -250,30 +249,36 @@ def interpret_level_by_phases(plan, k, x, inverse=False):
                     xs[prog['rowbase'][s]:prog['rowbase'][s] + d] = buf[s]
 
     def run_phase(T, inv):
-        assert T['max_rows'] * 32 * T['cols_per_lane'] * 8 <= 112 * 1024
-        ns = T['nstages']
-        for pi, (d, tiles, b_off, nb, pack) in enumerate(T['panels']):
+        blob = T['blob_inv' if inv else 'blob_fwd']
+        for pi, (d, tiles, g_off, ng, pack) in enumerate(T['panels']):
             assert d == dims[pi]
-            for bu in range(b_off, b_off + nb):
-                row_off, blk_off, st_off, nrows = (int(v) for v in T['bundles'][bu])
-                rows = T['rows'][row_off:row_off + nrows]
-                buf = np.stack([(ss[r[1]:r[1] + d] if (inv and r[2]) else xs[r[0]:r[0] + d]).copy() for r in rows])
-                sf = T['stage_first'][st_off:st_off + ns * 17].reshape(ns, 17)   # per stage: ranges of 16 warps
-                assert (np.diff(sf.reshape(-1)) >= 0).all()
-                for st in (range(ns - 1, -1, -1) if inv else range(ns)):
-                    seen = set()
-                    for b in range(blk_off + sf[st, 0], blk_off + sf[st, 16]):
-                        m = T['blocks'][b, 5]
-                        loc = [int(v) for v in T['blocks'][b, :m]]
-                        assert not (seen & set(loc)), 'blocks of one stage must touch disjoint rows'
-                        seen |= set(loc)
-                        at = T['blocks'][b, 7 if inv else 6]
-                        buf[loc] = coef[at:at + m * m].reshape(m, m) @ buf[loc]
-                for r, v in zip(rows, buf):
-                    if not inv and r[2]:
-                        ss[r[1]:r[1] + d] = v
+            for g in range(g_off, g_off + ng):
+                word0, words, nrows, nlow = (int(v) for v in T['groups'][g])
+                assert nrows <= T['max_rows'] and words <= T['max_blob']
+                raw = blob[16 * word0:16 * (word0 + words)]
+                table = raw[:8 * nrows].view(np.uint32)
+                xoff, dest = table[:nrows].astype(np.int64), table[nrows:].astype(np.int64)
+                # rows [0, nlow) live on the x side, rows [nlow, nrows) are finished in this phase
+                buf = np.stack([(ss[dest[r]:dest[r] + d] if (inv and r >= nlow) else xs[xoff[r]:xoff[r] + d]).copy()
+                                for r in range(nrows)])
+                at = 16 * ((2 * nrows + 3) // 4)
+                while True:
+                    hdr = raw[at:at + 16].view(np.uint16)
+                    m = int(hdr[5])
+                    if m == 0:
+                        break
+                    assert 2 <= m <= 5 and all(int(v) % 256 == 0 for v in hdr[:m])
+                    loc = [int(v) // 256 for v in hdr[:m]]
+                    assert len(set(loc)) == m and max(loc) < nrows
+                    cm = raw[at + 16:at + 16 + 8 * m * m].view(np.float64).reshape(m, m)
+                    buf[loc] = cm @ buf[loc]
+                    at += 16 + 16 * ((m * m + 1) // 2)
+                assert at + 16 == 16 * words
+                for r in range(nrows):
+                    if not inv and r >= nlow:
+                        ss[dest[r]:dest[r] + d] = buf[r]
                     else:
-                        xs[r[0]:r[0] + d] = v
+                        xs[xoff[r]:xoff[r] + d] = buf[r]
 
     if not inverse:
         low_stages(False)
