@@ -122,6 +122,11 @@ int snfft_coset_to_lex_host(const snfft_plan* plan, int64_t* out_host);
 int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
               double* out_dev, void* stream);
 
+/* The same in Young's SEMINORMAL form (yor.py:119-182 `ysemi` / `ysemi_t`): generator blocks
+ * [[1/d, 1 - 1/d^2], [1, -1/d]] on tableau pairs (t, t'), t before t'; same tables, same word. */
+int snfft_ysemi(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
+                double* out_dev, void* stream);
+
 /* Sampled inverse: f(sigma_j) for `count` permutations straight from ONE packed spectrum,
  * f(sigma) = (1/n!) sum_lambda d_lambda tr(rho_lambda(sigma)^T f_hat(lambda))
  * (tile/par_inv_ft.py:27-45 summed over the irreps; the per-state evaluation of
@@ -259,6 +264,10 @@ int64_t snfft_launch_count(void);
  * table-driven streaming kernel that serves k >= 9, so that tests can cover that kernel at a size
  * the oracle reaches. */
 int snfft_debug_force_table_driven(int on);
+/* A/B hook: the inverse fused kernel (levels 7..2) stages its input with ONE cp.async.bulk (1-D
+ * TMA) + mbarrier per S_7 spectrum (default, on != 0) or with 2 520 16-byte cp.async (on = 0);
+ * results are identical, the timing comparison (tools/ab_tma.py) is in profiles/README.md. */
+int snfft_debug_fused_tma(int on);
 
 /* Per-kernel timing for bench.py: when enabled, every launch of this library is bracketed by CUDA
  * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[15] and

@@ -51,10 +51,15 @@ def coset_reps(n, alpha):
 
 def cyclic_irrep(alpha, tup):
     """exp(2 pi i (0*p1 + 1*p2 + 2*p3) / 3) with p_k the sum of the k-th alpha-segment of tup
-    (wreath.py:123-143)."""
-    a, b = alpha[0], alpha[0] + alpha[1]
-    p2, p3 = sum(tup[a:b]), sum(tup[b:])
-    return np.exp(2j * np.pi * (p2 + 2 * p3) / 3.0)
+    (wreath.py:123-143).  For a weak partition into TWO parts this is the C_2 character
+    (+1 if p2 is even else -1) of the pyraminx group C2 wr S6 (pyraminx/px_wreath.py:17-23)."""
+    m, start, expo = len(alpha), 0, 0
+    for k, a in enumerate(alpha):
+        expo += k * sum(tup[start:start + a])
+        start += a
+    if m == 2:
+        return complex(1.0 if expo % 2 == 0 else -1.0)
+    return np.exp(2j * np.pi * expo / float(m))
 
 
 def block_cyclic_irreps(alpha, otup, reps):

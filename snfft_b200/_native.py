@@ -58,6 +58,7 @@ SIGNATURES = {
     "snfft_reorder": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),
     "snfft_coset_to_lex_host": (C.c_int, [_p, _p]),
     "snfft_yor": (C.c_int, [_p, C.c_int, _p, C.c_int64, _p, _p]),
+    "snfft_ysemi": (C.c_int, [_p, C.c_int, _p, C.c_int64, _p, _p]),
     "snfft_inverse_at": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p]),
     "snfft_dft_direct": (C.c_int, [_p, _p, _p, C.c_int64, _p]),
     "snfft_dft_release": (C.c_int, [_p]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "snfft_level_macs_per_element": (C.c_double, [_p, C.c_int]),
     "snfft_launch_count": (C.c_int64, []),
     "snfft_debug_force_table_driven": (C.c_int, [C.c_int]),
+    "snfft_debug_fused_tma": (C.c_int, [C.c_int]),
     "snfft_timing_enable": (C.c_int, [C.c_int]),
     "snfft_timing_read": (C.c_int, [_p, _p]),
     "snfft_export_panel": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

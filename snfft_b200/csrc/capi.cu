@@ -378,6 +378,19 @@ void upload_p1(snfft_plan* plan, int k) {
   build_p1_dev(plan->host.programs[k], lay, up, plan->p1_dev[k]);
 }
 
+// cudaFuncSetAttribute is per device: opt the kernels in to large dynamic shared memory once per
+// device, also for entry points that take no plan (snfft_dgemm, snfft_c3_dft, snfft_gather)
+void ensure_kernels_prepared() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) throw NoDevice("no CUDA device available");
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  CUDA_OK(prepare_kernels());
+  done[dev] = true;
+}
+
 template <class F>
 int guarded(F&& f) {
   try {
@@ -653,7 +666,7 @@ int snfft_plan_create(int n, int device, snfft_plan** out) {
       CUDA_OK(cudaGetDeviceProperties(&prop, device));
       if (prop.major < 10) throw NoDevice("snfft_b200 kernels are built for sm_100a only");
       plan->num_sms = prop.multiProcessorCount;
-      CUDA_OK(prepare_kernels());
+      ensure_kernels_prepared();
       for (int k = 2; k <= n; ++k) upload_level(plan, k);
       for (int k = kPhaseMinLevel; k <= n; ++k) {
         upload_phases(plan, k);
@@ -891,24 +904,34 @@ int snfft_coset_to_lex_host(const snfft_plan* plan, int64_t* out_host) {
   });
 }
 
-int snfft_yor(const snfft_plan* plan_, int irrep, const int32_t* perms_dev, int64_t count,
-              double* out_dev, void* stream) {
+namespace {
+void yor_impl(const snfft_plan* plan_, int irrep, const int32_t* perms_dev, int64_t count, double* out_dev,
+              bool seminormal, void* stream) {
   snfft_plan* plan = const_cast<snfft_plan*>(plan_);  // lazily cached generator tables
-  return guarded([&] {
-    require_device(plan);
-    const ShapeInfo& s = shape_of(plan, plan->host.n, irrep);
-    if (count < 0) throw InvalidArg("count < 0");
-    if (count == 0) return;
-    if (!perms_dev || !out_dev) throw InvalidArg("null device buffer");
-    DeviceGuard guard(plan->device);
-    if (plan->host.n == 1) {  // rho((1)) = [1]: identity "word" on a 1 x 1 matrix, no tables needed
-      CUDA_OK(launch_yor(1, 1, nullptr, nullptr, perms_dev, count, out_dev, (cudaStream_t)stream));
-      return;
-    }
-    YorTables& t = yor_tables_for(plan, irrep);
-    CUDA_OK(launch_yor(plan->host.n, (int)s.dim, t.partner, t.diag, perms_dev, count, out_dev,
-                       (cudaStream_t)stream));
-  });
+  require_device(plan);
+  const ShapeInfo& s = shape_of(plan, plan->host.n, irrep);
+  if (count < 0) throw InvalidArg("count < 0");
+  if (count == 0) return;
+  if (!perms_dev || !out_dev) throw InvalidArg("null device buffer");
+  DeviceGuard guard(plan->device);
+  if (plan->host.n == 1) {  // rho((1)) = [1]: identity "word" on a 1 x 1 matrix, no tables needed
+    CUDA_OK(launch_yor(1, 1, nullptr, nullptr, perms_dev, count, out_dev, seminormal, (cudaStream_t)stream));
+    return;
+  }
+  YorTables& t = yor_tables_for(plan, irrep);
+  CUDA_OK(launch_yor(plan->host.n, (int)s.dim, t.partner, t.diag, perms_dev, count, out_dev, seminormal,
+                     (cudaStream_t)stream));
+}
+}  // namespace
+
+int snfft_yor(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
+              double* out_dev, void* stream) {
+  return guarded([&] { yor_impl(plan, irrep, perms_dev, count, out_dev, false, stream); });
+}
+
+int snfft_ysemi(const snfft_plan* plan, int irrep, const int32_t* perms_dev, int64_t count,
+                double* out_dev, void* stream) {
+  return guarded([&] { yor_impl(plan, irrep, perms_dev, count, out_dev, true, stream); });
 }
 
 int snfft_inverse_at(const snfft_plan* plan_, const double* fhat_dev, const int32_t* perms_dev, int64_t count,
@@ -1396,6 +1419,7 @@ int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t
     if (!a_dev || !b_dev || !c_dev) throw InvalidArg("null device buffer");
     if (m < 0 || n < 0 || k < 0 || m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff)
       throw InvalidArg("bad GEMM shape");
+    ensure_kernels_prepared();
     CUDA_OK(launch_dgemm(a_dev, b_dev, c_dev, (int)m, (int)n, (int)k, (cudaStream_t)stream));
   });
 }
@@ -1407,6 +1431,7 @@ int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const 
     if (inverse && !in_im_dev) throw InvalidArg("the adjoint transform needs the imaginary plane");
     if (m < 1 || m > 9) throw InvalidArg("m must be in 1..9");
     if (nfreq < 1 || count < 0) throw InvalidArg("bad shape");
+    ensure_kernels_prepared();
     CUDA_OK(launch_c3_dft(m, in_re_dev, in_im_dev, freq_dev, nfreq, count, out_re_dev, out_im_dev, inverse != 0,
                           (cudaStream_t)stream));
   });
@@ -1489,6 +1514,11 @@ int64_t snfft_launch_count(void) { return g_launch_count; }
 
 int snfft_debug_force_table_driven(int on) {
   g_force_table_driven = on != 0;
+  return SNFFT_OK;
+}
+
+int snfft_debug_fused_tma(int on) {
+  g_fused_tma = on != 0;
   return SNFFT_OK;
 }
 

@@ -28,6 +28,7 @@ namespace snfft {
 
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<bool> g_force_table_driven{false};
+std::atomic<bool> g_fused_tma{true};  // measured 1.3 % faster than the LDGSTS stage-in (tools/ab_tma.py)
 
 namespace {
 struct TimedLaunch {
@@ -440,7 +441,40 @@ __device__ __forceinline__ void fused7_stage_async(double* Q, const double* gin)
   }
 }
 
-template <int K0, bool INV>
+// ---- TMA variant of the inverse stage-in (measured against the LDGSTS one, see profiles/README.md):
+// the 40 320 bytes of an S_7 spectrum are one contiguous, 16-byte aligned run, so ONE thread can
+// issue ONE bulk copy (cp.async.bulk, the 1-D form of TMA) that completes on an mbarrier, instead
+// of 2 520 16-byte cp.async spread over the CTA.  (The forward direction rotates the 16-byte chunks
+// of every S_4 block on the way in - see fused7_stage_async - which a bulk copy cannot do.)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int K0, bool INV, bool TMA = false>
 __global__ void __launch_bounds__(kFusedThreads, 2)
 fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in may alias out
   extern __shared__ double sm[];
@@ -448,10 +482,38 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
   double* P = sm;
   double* Q = sm + kFusedP;
   const int tid = threadIdx.x, nthreads = blockDim.x;
+  __shared__ unsigned long long stage_bar;
+  unsigned stage_parity = 0;
+  constexpr bool kBulk = TMA && INV && K0 == 7;
+  if (kBulk) {
+    if (tid == 0) mbar_init(&stage_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
+  auto stage_in = [&](const double* gsrc) {
+    if (kBulk) {
+      if (tid == 0) {
+        // the generic-proxy reads of this region by earlier phases are ordered by the barrier before
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&stage_bar, 5040 * 8);
+        bulk_g2s(Q + kFusedC, gsrc, 5040 * 8, &stage_bar);
+      }
+    } else {
+      fused7_stage_async<INV>(Q, gsrc);
+    }
+  };
+  auto stage_wait = [&]() {
+    if (kBulk) {
+      mbar_wait(&stage_bar, stage_parity);
+      stage_parity ^= 1u;
+    } else {
+      cp_async_wait_all();
+    }
+  };
 
   if (K0 == 7 && (int64_t)blockIdx.x < groups) {
-    fused7_stage_async<INV>(Q, in + (int64_t)blockIdx.x * S::kFact);
-    cp_async_wait_all();
+    stage_in(in + (int64_t)blockIdx.x * S::kFact);
+    stage_wait();
     __syncthreads();
   }
   for (int64_t g0 = (int64_t)blockIdx.x * S::kGroups; g0 < groups; g0 += (int64_t)gridDim.x * S::kGroups) {
@@ -542,7 +604,7 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
         // ---- level 7 as two register phases ---------------------------------------------------
         __syncthreads();
         SNFFT_PH(3)
-        if (gnext < groups) fused7_stage_async<false>(Q, in + gnext * S::kFact);
+        if (gnext < groups) stage_in(in + gnext * S::kFact);
         fused_level7_phase1<false>(P, Q);
         __syncthreads();
         SNFFT_PH(4)
@@ -586,7 +648,7 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
               [&](int g) { return P + g * gen::kG5; });
         __syncthreads();
         SNFFT_PH(9)
-        if (K0 == 7 && gnext < groups) fused7_stage_async<true>(Q, in + gnext * S::kFact);
+        if (K0 == 7 && gnext < groups) stage_in(in + gnext * S::kFact);
       }
       if (K0 == 4) {
         for (int e = tid; e < nelem; e += nthreads) {
@@ -612,8 +674,8 @@ fused_kernel(FusedDev F, const double* in, double* out, int64_t groups) {  // in
         gout[e] = P[b * gen::kS4 + (e - b * 24)];
       }
     }
-    if (K0 == 7) cp_async_wait_all();  // the next chunk's input has landed
-    __syncthreads();                   // buffers are reused by the next chunk
+    if (K0 == 7 && (!kBulk || gnext < groups)) stage_wait();  // the next chunk's input has landed
+    __syncthreads();                                          // buffers are reused by the next chunk
     SNFFT_PH(12)
   }
 }
@@ -1153,6 +1215,9 @@ reorder_tiled_kernel(int n, Facts F, int nsubsets, int64_t nmid, int mids_per_ct
 // ---------------------------------------------------------------------------------------------
 // rho_lambda(sigma): apply the generator word to the identity, one CTA per permutation
 // ---------------------------------------------------------------------------------------------
+// SEMI: Young's seminormal form (yor.py:119-182): for a tableau pair (r, q), r < q, the generator
+// block is [[a, 1 - a^2], [1, -a]] instead of the orthogonal [[a, b], [b, -a]], b = sqrt(1 - a^2).
+template <bool SEMI>
 __global__ void __launch_bounds__(kThreads)
 yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __restrict__ diag,
            const int32_t* __restrict__ perms, double* __restrict__ out) {
@@ -1192,10 +1257,10 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
       if (q < 0) {
         M[e] = a * M[e];
       } else if (q > r) {
-        const double b = sqrt(1 - a * a);
+        const double b = SEMI ? 1 - a * a : sqrt(1 - a * a);
         const double x = M[(int64_t)r * d + c], y = M[(int64_t)q * d + c];
         M[(int64_t)r * d + c] = a * x + b * y;
-        M[(int64_t)q * d + c] = b * x - a * y;
+        M[(int64_t)q * d + c] = (SEMI ? x : b * x) - a * y;
       }
     }
     __syncthreads();
@@ -1609,6 +1674,8 @@ cudaError_t prepare_kernels() {
   if ((e = allow_big_smem(phase_kernel<true, 1>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 2>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<true, 2>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<false, 4>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(phase_kernel<true, 4>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level8_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<4, false>)) != cudaSuccess) return e;
@@ -1619,6 +1686,7 @@ cudaError_t prepare_kernels() {
   if ((e = allow_big_smem(fused_kernel<6, true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<7, false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(fused_kernel<7, true>)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(fused_kernel<7, true, true>, 200)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1683,7 +1751,10 @@ static cudaError_t launch_fused_k0(const FusedDev& F, const double* in, double* 
   int64_t grid = (groups + per_iter - 1) / per_iter;
   if (grid > 2LL * num_sms * SNFFT_FUSED_WAVES) grid = 2LL * num_sms * SNFFT_FUSED_WAVES;  // persistent beyond that
   LaunchScope scope(inverse ? kKindFusedInv : kKindFusedFwd, stream);
-  if (inverse)
+  if (inverse && K0 == 7 && g_fused_tma.load(std::memory_order_relaxed) &&
+      (reinterpret_cast<uintptr_t>(in) & 15) == 0)
+    fused_kernel<7, true, true><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
+  else if (inverse)
     fused_kernel<K0, true><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
   else
     fused_kernel<K0, false><<<(unsigned)grid, kFusedThreads, smem, stream>>>(F, in, out, groups);
@@ -1702,8 +1773,13 @@ cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const i
   int A = 1;
   {
     const size_t two = ((size_t)P.max_rows * 64 + P.max_blob * 2) * sizeof(double);
+    const size_t four = ((size_t)P.max_rows * 128 + P.max_blob * 2) * sizeof(double);
     if ((226 * 1024) / two >= 6) A = 2;
-    if (const char* env = std::getenv("SNFFT_PHASE_A")) A = std::atoi(env) == 2 ? 2 : 1;
+    if ((226 * 1024) / four >= 8) A = 4;
+    if (const char* env = std::getenv("SNFFT_PHASE_A")) {
+      const int want = std::atoi(env);
+      if (want == 1 || want == 2 || (want == 4 && (226 * 1024) / four >= 1)) A = want;
+    }
   }
   const int warp_doubles = P.max_rows * 32 * A + P.max_blob * 2;
   int nwarps = (int)((226 * 1024) / ((size_t)warp_doubles * sizeof(double)));
@@ -1738,12 +1814,16 @@ cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const i
   const size_t smem = (size_t)nwarps * warp_doubles * sizeof(double);
   LaunchScope scope(inverse ? kKindPhaseInv : kKindPhaseFwd, stream);
   if (inverse) {
-    if (A == 2)
+    if (A == 4)
+      phase_kernel<true, 4><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
+    else if (A == 2)
       phase_kernel<true, 2><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
     else
       phase_kernel<true, 1><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
   } else {
-    if (A == 2)
+    if (A == 4)
+      phase_kernel<false, 4><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
+    else if (A == 2)
       phase_kernel<false, 2><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
     else
       phase_kernel<false, 1><<<(unsigned)grid, nwarps * 32, smem, stream>>>(P, Lp, xside, sside, (uint32_t)lgroups, warp_doubles);
@@ -1842,10 +1922,13 @@ cudaError_t launch_reorder(int n, const uint32_t* table, const double* src, doub
 }
 
 cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
-                       const int32_t* perms, int64_t count, double* out, cudaStream_t stream) {
+                       const int32_t* perms, int64_t count, double* out, bool seminormal, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
   LaunchScope scope(kKindYor, stream);
-  yor_kernel<<<(unsigned)count, kThreads, 0, stream>>>(n, d, partner, diag, perms, out);
+  if (seminormal)
+    yor_kernel<true><<<(unsigned)count, kThreads, 0, stream>>>(n, d, partner, diag, perms, out);
+  else
+    yor_kernel<false><<<(unsigned)count, kThreads, 0, stream>>>(n, d, partner, diag, perms, out);
   return cudaGetLastError();
 }
 

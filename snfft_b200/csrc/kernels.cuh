@@ -11,6 +11,7 @@ namespace snfft {
 
 extern std::atomic<int64_t> g_launch_count;
 extern std::atomic<bool> g_force_table_driven;  // tests: route level 8 through the table-driven kernel too
+extern std::atomic<bool> g_fused_tma;           // experiment: TMA bulk stage-in of the inverse fused kernel
 
 // Optional per-launch timing (bench.py): when enabled every launch is bracketed by CUDA events on
 // its own stream; timing_read() synchronises the recorded events and returns the totals per kind.
@@ -51,7 +52,7 @@ cudaError_t launch_build_lex_table(int n, uint32_t* table, cudaStream_t stream);
 // rho_lambda(sigma) for a list of permutations: rows tables are int32 partner[(n-1)][d] and
 // double diag[(n-1)][d] for the generators s_1..s_{n-1} of one irrep.
 cudaError_t launch_yor(int n, int d, const int32_t* partner, const double* diag,
-                       const int32_t* perms, int64_t count, double* out, cudaStream_t stream);
+                       const int32_t* perms, int64_t count, double* out, bool seminormal, cudaStream_t stream);
 
 // f(sigma_j) for `count` permutations from one packed spectrum (all irreps in one launch); out is zeroed first.
 cudaError_t launch_inverse_at(int n, const InvAtItem* items, int nitems, const InvAtIrrep* irreps, size_t smem_bytes,

@@ -196,8 +196,9 @@ class Plan:
                                         int(bool(to_coset)), self._stream()))
         return out
 
-    def yor(self, irrep: int, perms):
-        """rho_lambda(sigma) for int32 CUDA tensor perms [count, n] -> [count, d, d]."""
+    def yor(self, irrep: int, perms, seminormal: bool = False):
+        """rho_lambda(sigma) for int32 CUDA tensor perms [count, n] -> [count, d, d] in Young's
+        orthogonal form, or (``seminormal=True``) in the seminormal form of yor.py:119-182."""
         import torch
         if perms.dtype != torch.int32 or not perms.is_cuda or not perms.is_contiguous():
             raise TypeError("perms must be a contiguous int32 CUDA tensor")
@@ -206,8 +207,8 @@ class Plan:
         d = self.layout()[1][irrep]
         out = torch.empty((perms.shape[0], d, d), dtype=torch.float64, device=perms.device)
         with torch.cuda.device(self.device):
-            N.check(N.lib.snfft_yor(self._h, irrep, N.ptr(perms), perms.shape[0], N.ptr(out),
-                                    self._stream()))
+            fn = N.lib.snfft_ysemi if seminormal else N.lib.snfft_yor
+            N.check(fn(self._h, irrep, N.ptr(perms), perms.shape[0], N.ptr(out), self._stream()))
         return out
 
     def inverse_at(self, fhat, perms):

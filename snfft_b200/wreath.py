@@ -102,12 +102,21 @@ class WreathCycSn:
 
 # ---- characters and induced blocks (wreath.py:43-58, :123-143, :175-224, :281-343, :387-394) -------
 def cyclic_irreps(weak_partition):
-    """tup -> exp(2 pi i (1*p2 + 2*p3)/3), p_k = sum of the k-th alpha-segment of tup."""
-    a, b = weak_partition[0], weak_partition[0] + weak_partition[1]
+    """tup -> exp(2 pi i (1*p2 + 2*p3)/3), p_k = sum of the k-th alpha-segment of tup
+    (wreath.py:123-143).  A weak partition into two parts gives the C_2 characters (+-1) of the
+    pyraminx group C2 wr S6 (pyraminx/px_wreath.py:17-23, ``cyc_irr_func``)."""
+    m = len(weak_partition)
+    seg = np.repeat(np.arange(m), weak_partition)
 
     def func(tup):
-        return np.exp(2j * np.pi * (sum(tup[a:b]) + 2 * sum(tup[b:])) / 3.)
+        expo = int(np.dot(seg, np.asarray(tup)))
+        if m == 2:
+            return 1.0 if expo % 2 == 0 else -1.0
+        return np.exp(2j * np.pi * expo / float(m))
     return func
+
+
+cyc_irr_func = cyclic_irreps   # the name pyraminx/px_wreath.py uses
 
 
 def block_cyclic_irreps(tup, coset_reps, cyclic_irrep_func):
@@ -193,7 +202,7 @@ def _lex_ranks(perms):
 
 
 def orientation_mode(oris, n):
-    """How the orientation axis is laid out: 'zero_sum' = the tuples of {0,1,2}^n with sum = 0 mod 3
+    """How the orientation axis of a C_3 group is laid out: 'zero_sum' = the tuples of {0,1,2}^n with sum = 0 mod 3
     in itertools.product order (utils.py:206-209: the index is the base-3 number of the first n-1
     letters), 'full' = all 3^n tuples in product order, None = anything else."""
     oris = np.asarray(oris, dtype=np.int64).reshape(-1, n)
@@ -253,9 +262,10 @@ def _alpha_tables(alpha, device):
 
 
 class WreathPlan:
-    """Fourier transform of functions on C_3^n x S_n (orientations restricted to ``oris``) at one
-    irrep (alpha, parts).  f is a float64 CUDA tensor [n!, len(oris)]: sigma in ``sn(n)`` order
-    (slow axis), orientation index (fast axis).
+    """Fourier transform of functions on C_m^n x S_n (orientations restricted to ``oris``) at one
+    irrep (alpha, parts); m = len(alpha): 3 for the 2x2 cube group C3 wr S8 (wreath.py), 2 for the
+    pyraminx group C2 wr S6 (pyraminx/px_wreath.py).  f is a float64 CUDA tensor [n!, len(oris)]:
+    sigma in ``sn(n)`` order (slow axis), orientation index (fast axis).
 
     Stage 1 (character sums over the orientations) is a radix-3 DFT over C_3^m in shared memory
     (``snfft_c3_dft``: one pass over f) whenever the orientation axis is the standard one
@@ -272,21 +282,26 @@ class WreathPlan:
         self.N = len(self.reps)
         self.block = wreath_dim(self.parts)
         self.D = self.N * self.block
+        self.cyc_order = m = len(self.alpha)
         if oris is None:
-            oris = [t for t in itertools.product((0, 1, 2), repeat=n) if sum(t) % 3 == 0]   # utils.py:206-209
+            if m == 3:
+                oris = [t for t in itertools.product((0, 1, 2), repeat=n) if sum(t) % 3 == 0]   # utils.py:206-209
+            else:
+                oris = list(itertools.product(range(m), repeat=n))
         self.oris = np.array(oris, dtype=np.int64).reshape(-1, n)
         self.order = math.factorial(n) * len(self.oris)
-        self.mode = orientation_mode(self.oris, n)
+        self.mode = orientation_mode(self.oris, n) if m == 3 else None
+        self.seg = np.repeat(np.arange(m), self.alpha)               # segment of position p
         T = tabs['T']
         if self.mode is not None:
             self.dft_m = n if self.mode == 'full' else n - 1
             self.freq = torch.from_numpy(dft_frequencies(self.alpha, self.reps, self.mode)).to(dev)
         else:
-            # characters chi_i(o) (wreath.py:34-58): o o t_i summed over the alpha-segments
-            a, b = self.alpha[0], self.alpha[0] + self.alpha[1]
+            # characters chi_i(o) (wreath.py:34-58): o o t_i summed over the alpha-segments, the
+            # k-th segment weighted by k (px_wreath.py:17-30 for two segments)
             og = self.oris[:, T - 1]                                      # [n_ori, N, n]
-            expo = (og[:, :, a:b].sum(-1) + 2 * og[:, :, b:].sum(-1)) % 3
-            omega = np.exp(2j * np.pi * np.arange(3) / 3.)
+            expo = (og * self.seg).sum(-1) % m
+            omega = np.exp(2j * np.pi * np.arange(m) / float(m)) if m != 2 else np.array([1.0 + 0j, -1.0 + 0j])
             X = omega[expo]                                               # [n_ori, N]
             self.Xre = torch.from_numpy(np.ascontiguousarray(X.real)).to(dev)
             self.Xim = torch.from_numpy(np.ascontiguousarray(X.imag)).to(dev)
@@ -389,10 +404,10 @@ class WreathPlan:
         b, N_ = self.block, self.N
         T = np.array(self.reps, dtype=np.int64)
         index = {tuple(t): i for i, t in enumerate(self.reps)}
-        seg = np.repeat(np.arange(3), self.alpha)
-        a_, b_ = self.alpha[0], self.alpha[0] + self.alpha[1]
+        m = self.cyc_order
+        bounds = np.cumsum((0,) + self.alpha)
         blocks = fhat.reshape(N_, b, N_, b).permute(0, 2, 1, 3)       # [i, j, b, b]
-        omega = np.exp(2j * np.pi * np.arange(3) / 3.)
+        omega = np.exp(2j * np.pi * np.arange(m) / float(m)) if m != 2 else np.array([1.0 + 0j, -1.0 + 0j])
         Hlist = [p.tup_rep for p in young_subgroup_perm(self.alpha)]
         hindex = {h: q for q, h in enumerate(Hlist)}
         out = []
@@ -402,13 +417,13 @@ class WreathPlan:
             ii, hh = [], []
             for j in range(N_):
                 st = sig[T[j] - 1]                                    # sigma t_j
-                rep = np.concatenate([np.sort(st[:a_]), np.sort(st[a_:b_]), np.sort(st[b_:])])
+                rep = np.concatenate([np.sort(st[bounds[k]:bounds[k + 1]]) for k in range(m)])
                 i = index[tuple(int(v) for v in rep)]
                 h = tuple(int(v) for v in (np.argsort(T[i]) + 1)[st - 1])   # t_i^-1 sigma t_j
                 ii.append(i)
                 hh.append(hindex[h])
             o = np.array(ori, dtype=np.int64)
-            expo = (o[T[ii][:, a_:b_] - 1].sum(-1) + 2 * o[T[ii][:, b_:] - 1].sum(-1)) % 3
+            expo = (o[T[ii] - 1] * self.seg).sum(-1) % m
             chi = torch.from_numpy(omega[expo]).to(dev)               # D(o)_ii
             it = torch.tensor(ii, device=dev)
             jt = torch.arange(N_, device=dev)

@@ -98,6 +98,17 @@ def yor_batch(ferrers, tuples, device=0):
     return out.cpu().numpy()
 
 
+def ysemi_batch(ferrers, tuples, device=0):
+    """Seminormal-form matrices of a list of permutation tuples on the device (``snfft_ysemi``)
+    -> ndarray [count, d, d]; the host functions below are the reference-shaped entry points."""
+    import torch
+    n = ferrers.size
+    plan = get_plan(n, device)
+    perms = torch.tensor([_full_tuple(t, n) for t in tuples], dtype=torch.int32,
+                         device=f'cuda:{device}').reshape(-1, n)
+    return plan.yor(plan.irrep_index(ferrers.partition), perms, seminormal=True).cpu().numpy()
+
+
 # ---- Young's seminormal form (reference yor.py:119-182); small host-side helper, not on the hot path
 def ysemi_t(f, transposition):
     """Seminormal matrix of the adjacent transposition (k, k+1): for a tableau t whose swap t' is

@@ -111,6 +111,27 @@ def test_sampled_inverse_against_the_oracle(n):
     assert np.abs(got - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
 
 
+def test_device_seminormal_form_matches_host_and_reference_known_answers():
+    """snfft_ysemi (Young's seminormal form on the device, yor.py:119-182) against the host mirror
+    (pinned to the reference's own known answers, test.py:53-64) on random permutations, plus the
+    homomorphism property at n = 7."""
+    from snfft_b200.yor import ysemi, ysemi_batch
+    rng = np.random.default_rng(12)
+    for p in [(3, 1), (2, 2), (3, 2, 1), (4, 1, 1), (2, 2, 1, 1)]:
+        n = sum(p)
+        fd = FerrersDiagram(p)
+        tups = [tuple(int(x) + 1 for x in rng.permutation(n)) for _ in range(6)] + [tuple(range(1, n + 1))]
+        got = ysemi_batch(fd, tups)
+        for t, m in zip(tups, got):
+            assert np.allclose(m, ysemi(fd, Perm2.from_tup(t)), atol=1e-13, rtol=0)
+    fd = FerrersDiagram((3, 2, 2))
+    g = tuple(int(x) + 1 for x in rng.permutation(7))
+    h = tuple(int(x) + 1 for x in rng.permutation(7))
+    gh = (Perm2.from_tup(g) * Perm2.from_tup(h)).tup_rep
+    mg, mh, mgh = ysemi_batch(fd, [g, h, gh])
+    assert np.allclose(mg @ mh, mgh, atol=1e-12, rtol=0)
+
+
 def test_sampled_inverse_and_file_job(tmp_path):
     # tile/par_inv_ft.py:27-45 per state, summed over irreps; s8fft.do_all_ffts from a text table
     from snfft_b200 import io

@@ -171,3 +171,34 @@ def test_sampled_wreath_inverse_against_oracle(ci):
     # and the dense device inverse agrees with the sampled one on the cube-sized path too
     dense = wp.inverse(torch.from_numpy(fhat).cuda()).cpu().numpy()
     assert np.abs(dense - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+
+
+def test_pyraminx_group_c2_wr_sn():
+    """Row f4: the same transform for the pyraminx group C2 wr S_n (pyraminx/px_wreath.py): irreps
+    indexed by a weak partition into TWO parts, characters +-1.  Parity against the oracle on
+    C2 wr S5 and Plancherel over all irreps of C2 wr S4 (sum D^2 = 2^4 4!)."""
+    from snfft_b200.utils import partition_parts, weak_partitions
+    n = 5
+    oris = W.orientations(n, order=2, zero_sum=False)
+    f = np.random.default_rng(26).standard_normal((math.factorial(n), len(oris)))
+    for alpha, parts in [((2, 3), ((1, 1), (2, 1))), ((4, 1), ((2, 2), (1,))), ((0, 5), ((), (3, 2)))]:
+        wp = WreathPlan(alpha, parts, oris=oris)
+        got = wp.forward(torch.from_numpy(f).cuda()).cpu().numpy()
+        ref = W.wreath_ft_direct(alpha, parts, f, oris)
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10
+        assert np.abs(got.imag).max() < 1e-12
+        inv = wp.inverse(torch.from_numpy(ref).cuda()).cpu().numpy()
+        want = W.wreath_inverse_direct(alpha, parts, ref, oris, math.factorial(n) * len(oris))
+        assert np.abs(inv - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+    n = 4
+    oris = W.orientations(n, order=2, zero_sum=False)
+    f = np.random.default_rng(27).standard_normal((24, len(oris)))
+    fd = torch.from_numpy(f).cuda()
+    total, dims = 0.0, 0
+    for alpha in weak_partitions(n, 2):
+        for parts in partition_parts(alpha):
+            wp = WreathPlan(alpha, parts, oris=oris)
+            total += wp.D * (wp.forward(fd).abs() ** 2).sum().item()
+            dims += wp.D ** 2
+    assert dims == 24 * 16
+    assert abs(total - 24 * 16 * (f ** 2).sum()) / total < 1e-12
