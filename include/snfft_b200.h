@@ -232,6 +232,31 @@ int snfft_forward_sharded(snfft_shard* shard, const double* f_local_dev, double*
 int snfft_inverse_sharded(snfft_shard* shard, const double* fhat_compact_dev, double* f_local_dev,
                           const snfft_shard_ws* ws, void* stream);
 
+/* ---- Wreath-product transform (C3 wr S_n: the 2x2 cube group for n = 8) as one object -----------
+ * f_hat = sum_{(o, sigma)} f(sigma, o) rho(o, sigma) at the irrep (alpha, parts) (multi.py:25-46,
+ * cube_ft.py:33-73 with the irrep matrices of wreath.py:281-343): rho = D(o) Ind_{S_alpha}^{S_n}
+ * (kron_k rho_{parts_k}).  The plan builds on the device what the reference pickles per irrep: coset
+ * representatives of the Young subgroup (coset_utils.py:72-100), the frequencies of the characters
+ * (wreath.py:43-58, :123-143), kron_k rho_{parts_k}(h) for h in S_alpha (wreath.py:191-224) and the
+ * index of sigma = t_i h t_j^-1 for every coset pair.  alpha: int32[3], a weak partition of n;
+ * parts: int32[3][n], the three partitions zero-padded to n entries; all_orientations = 0: the
+ * orientation axis holds the 3^(n-1) tuples with zero sum mod 3 in product order (utils.py:206-209:
+ * index = base-3 number of the first n-1 letters), != 0: all 3^n tuples.  n <= 9.
+ * f_dev: double[n!][orientations], sigma in perm2.sn order (lexicographic).  Output: the complex
+ * D x D matrix as two row-major planes (D = cosets x block).  A plan serialises its transforms
+ * (one shared workspace).  dims int64[6] = {D, cosets N, block, |S_alpha|, n!, orientations}. */
+typedef struct snfft_wreath snfft_wreath;
+int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int all_orientations, int device,
+                        snfft_wreath** out);
+int snfft_wreath_destroy(snfft_wreath* plan);
+int snfft_wreath_dims(const snfft_wreath* plan, int64_t* dims);
+int snfft_wreath_forward(snfft_wreath* plan, const double* f_dev, double* out_re_dev, double* out_im_dev,
+                         void* stream);
+/* D tr(rho(g)^H f_hat) / |G| at every group element (cube_ift.py:56-67, fft.py:158-172 divided by
+ * the group order): out planes double[n!][orientations]. */
+int snfft_wreath_inverse(snfft_wreath* plan, const double* fhat_re_dev, const double* fhat_im_dev,
+                         double* out_re_dev, double* out_im_dev, void* stream);
+
 /* ---- Building blocks of the wreath-product transform (wreath.py / multi.py / cube_ft.py) -------
  * C[m,n] = A[m,k] B[k,n], fp64 row-major device matrices, on the DMMA tensor pipe
  * (mma.sync.m8n8k4.f64).  The direct sums sum_g f(g) rho(g) of multi.py:25-46 and the character

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1421,6 +1422,301 @@ int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t
       throw InvalidArg("bad GEMM shape");
     ensure_kernels_prepared();
     CUDA_OK(launch_dgemm(a_dev, b_dev, c_dev, (int)m, (int)n, (int)k, (cudaStream_t)stream));
+  });
+}
+
+}  // extern "C"
+
+// -----------------------------------------------------------------------------------------------
+// wreath-product transform as one C object (snfft_wreath_forward)
+// -----------------------------------------------------------------------------------------------
+struct snfft_wreath {
+  int n = 0, device = -1, m = 0;  // m = digits of the orientation DFT (n - 1 for zero-sum orientations, n for all)
+  int alpha[3] = {0, 0, 0};
+  int64_t N = 0, nH = 0, block = 0, D = 0, nfact = 0, n_ori = 0;
+  int32_t* freq = nullptr;
+  int64_t *idx = nullptr, *inv_idx = nullptr;
+  double *R = nullptr, *RT = nullptr;                      // [nH][b*b] and its transpose
+  double *Fre = nullptr, *Fim = nullptr, *G = nullptr, *P = nullptr;  // workspace
+  std::vector<void*> allocs;
+  std::vector<snfft_plan*> factor_plans;
+  std::mutex mu;  // one transform at a time per plan (the workspace is shared)
+
+  template <class T>
+  T* alloc(size_t count) {
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    allocs.push_back(p);
+    return (T*)p;
+  }
+  template <class T>
+  T* upload(const std::vector<T>& v) {
+    T* p = alloc<T>(v.size());
+    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+  }
+};
+
+extern "C" {
+
+int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int all_orientations, int device,
+                        snfft_wreath** out) {
+  if (!out) {
+    g_last_error = "out is null";
+    return SNFFT_ERR_INVALID;
+  }
+  *out = nullptr;
+  snfft_wreath* w = nullptr;
+  int rc = guarded([&] {
+    if (!alpha || !parts) throw InvalidArg("null argument");
+    if (n < 1 || n > 9) throw InvalidArg("n must be in 1..9");
+    if (alpha[0] < 0 || alpha[1] < 0 || alpha[2] < 0 || alpha[0] + alpha[1] + alpha[2] != n)
+      throw InvalidArg("alpha must be a weak partition of n into three parts");
+    if (device < 0) throw NoDevice("the wreath transform needs a CUDA device; there is no CPU fallback");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count)
+      throw NoDevice("CUDA device " + std::to_string(device) + " is not available");
+    DeviceGuard guard(device);
+    ensure_kernels_prepared();
+    w = new snfft_wreath();
+    w->n = n;
+    w->device = device;
+    w->m = all_orientations ? n : n - 1;
+    if (w->m < 1) throw InvalidArg("the zero-sum orientation group of C_3 wr S_1 is trivial");
+    for (int k = 0; k < 3; ++k) w->alpha[k] = alpha[k];
+    w->nfact = 1;
+    for (int i = 2; i <= n; ++i) w->nfact *= i;
+    w->n_ori = 1;
+    for (int i = 0; i < w->m; ++i) w->n_ori *= 3;
+    // ---- coset representatives t_i of S_alpha: letters ascending inside every alpha-segment, in
+    // lexicographic order (coset_utils.py:72-100) ----
+    std::vector<std::vector<int8_t>> reps;
+    {
+      std::vector<int8_t> cur;
+      std::vector<char> used(n + 1, 0);
+      std::function<void(int, int, int)> rec = [&](int seg, int filled, int last) {
+        if (seg == 3) {
+          reps.push_back(cur);
+          return;
+        }
+        if (filled == alpha[seg]) {
+          rec(seg + 1, 0, 0);
+          return;
+        }
+        for (int v = last + 1; v <= n; ++v)
+          if (!used[v]) {
+            used[v] = 1;
+            cur.push_back((int8_t)v);
+            rec(seg, filled + 1, v);
+            cur.pop_back();
+            used[v] = 0;
+          }
+      };
+      rec(0, 0, 0);
+      std::sort(reps.begin(), reps.end());
+    }
+    w->N = (int64_t)reps.size();
+    std::vector<int8_t> T((size_t)w->N * n), Tinv((size_t)w->N * n);
+    std::vector<int32_t> freq((size_t)w->N);
+    int seg_of[kMaxN];
+    for (int p = 0, k = 0, c = 0; p < n; ++p) {
+      while (c == alpha[k]) {
+        ++k;
+        c = 0;
+      }
+      seg_of[p] = k;
+      ++c;
+    }
+    for (int64_t i = 0; i < w->N; ++i) {
+      int e[kMaxN];
+      for (int p = 0; p < n; ++p) {
+        T[i * n + p] = reps[i][p];
+        Tinv[i * n + reps[i][p] - 1] = (int8_t)(p + 1);
+        e[reps[i][p] - 1] = seg_of[p];  // chi_i(o) = omega^{sum_q e(q) o_q}, e(t_i(p)) = segment of p
+      }
+      int32_t f = 0;
+      for (int q = 0; q < w->m; ++q) f = f * 3 + (all_orientations ? e[q] : ((e[q] - e[n - 1]) % 3 + 3) % 3);
+      freq[i] = f;
+    }
+    // ---- Young subgroup S_alpha in itertools.product order, and R[h] = kron_k rho_{parts_k}(h_k) ----
+    std::vector<std::vector<std::vector<int>>> seg_perms(3);
+    std::vector<std::vector<double>> seg_mats(3);  // [a_k!][d_k * d_k] on the host
+    std::vector<int> seg_dim(3, 1);
+    int nontrivial = 0, only = -1;
+    double* single_dev = nullptr;
+    for (int k = 0; k < 3; ++k) {
+      const int a = alpha[k];
+      std::vector<int> p(a);
+      for (int i = 0; i < a; ++i) p[i] = i + 1;
+      do seg_perms[k].push_back(p); while (std::next_permutation(p.begin(), p.end()));
+      if (a == 0) {
+        seg_mats[k] = {1.0};
+        continue;
+      }
+      ++nontrivial;
+      only = k;
+    }
+    w->nH = (int64_t)seg_perms[0].size() * seg_perms[1].size() * seg_perms[2].size();
+    if (w->N * w->nH != w->nfact) throw std::runtime_error("coset count times subgroup order != n!");
+    for (int k = 0; k < 3; ++k) {
+      const int a = alpha[k];
+      if (a == 0) continue;
+      snfft_plan* fp = nullptr;
+      if (snfft_plan_create(a, device, &fp) != SNFFT_OK) throw CudaError(g_last_error);
+      w->factor_plans.push_back(fp);
+      const auto& shapes = fp->host.levels[a].shapes;
+      int irrep = -1;
+      for (size_t i = 0; i < shapes.size(); ++i) {
+        bool same = true;
+        for (int q = 0; q < n; ++q) {
+          const int want = parts[k * n + q];
+          const int have = q < (int)shapes[i].rows.size() ? shapes[i].rows[q] : 0;
+          if (want != have) same = false;
+        }
+        if (same) irrep = (int)i;
+      }
+      if (irrep < 0) throw InvalidArg("parts[" + std::to_string(k) + "] is not a partition of alpha[" + std::to_string(k) + "]");
+      const int64_t d = shapes[irrep].dim, cnt = (int64_t)seg_perms[k].size();
+      seg_dim[k] = (int)d;
+      std::vector<int32_t> flat((size_t)cnt * a);
+      for (int64_t r = 0; r < cnt; ++r)
+        for (int q = 0; q < a; ++q) flat[r * a + q] = seg_perms[k][r][q];
+      int32_t* perms_dev = w->upload(flat);
+      double* mats_dev = w->alloc<double>((size_t)cnt * d * d);
+      if (snfft_yor(fp, irrep, perms_dev, cnt, mats_dev, nullptr) != SNFFT_OK) throw CudaError(g_last_error);
+      CUDA_OK(cudaDeviceSynchronize());
+      if (nontrivial == 1) {
+        single_dev = mats_dev;  // R is this factor's table itself
+      } else {
+        seg_mats[k].resize((size_t)cnt * d * d);
+        CUDA_OK(cudaMemcpy(seg_mats[k].data(), mats_dev, seg_mats[k].size() * sizeof(double), cudaMemcpyDeviceToHost));
+      }
+    }
+    w->block = (int64_t)seg_dim[0] * seg_dim[1] * seg_dim[2];
+    w->D = w->N * w->block;
+    const int64_t bb = w->block * w->block;
+    if (nontrivial == 1) {
+      (void)only;
+      w->R = single_dev;
+    } else {
+      std::vector<double> R((size_t)w->nH * bb);
+      const int d0 = seg_dim[0], d1 = seg_dim[1], d2 = seg_dim[2];
+      int64_t h = 0;
+      for (size_t x = 0; x < seg_perms[0].size(); ++x)
+        for (size_t y = 0; y < seg_perms[1].size(); ++y)
+          for (size_t z = 0; z < seg_perms[2].size(); ++z, ++h) {
+            const double* A = &seg_mats[0][x * d0 * d0];
+            const double* B = &seg_mats[1][y * d1 * d1];
+            const double* Cm = &seg_mats[2][z * d2 * d2];
+            double* dst = &R[h * bb];
+            for (int a0 = 0; a0 < d0; ++a0)
+              for (int a1 = 0; a1 < d1; ++a1)
+                for (int a2 = 0; a2 < d2; ++a2)
+                  for (int c0 = 0; c0 < d0; ++c0)
+                    for (int c1 = 0; c1 < d1; ++c1)
+                      for (int c2 = 0; c2 < d2; ++c2)
+                        dst[(((int64_t)a0 * d1 + a1) * d2 + a2) * w->block + ((int64_t)c0 * d1 + c1) * d2 + c2] =
+                            A[a0 * d0 + c0] * B[a1 * d1 + c1] * Cm[a2 * d2 + c2];
+          }
+      w->R = w->upload(R);
+    }
+    w->RT = w->alloc<double>((size_t)w->nH * bb);
+    CUDA_OK(launch_transpose(w->R, w->RT, w->nH, bb, nullptr));
+    // ---- gather index sigma = t_i h t_j^-1 and its inverse, on the device ----
+    std::vector<int8_t> H((size_t)w->nH * n);
+    {
+      int64_t h = 0;
+      for (const auto& x : seg_perms[0])
+        for (const auto& y : seg_perms[1])
+          for (const auto& z : seg_perms[2]) {
+            int at = 0;
+            for (int v : x) H[h * n + at++] = (int8_t)v;
+            for (int v : y) H[h * n + at++] = (int8_t)(alpha[0] + v);
+            for (int v : z) H[h * n + at++] = (int8_t)(alpha[0] + alpha[1] + v);
+            ++h;
+          }
+    }
+    int8_t* T_dev = w->upload(T);
+    int8_t* Tinv_dev = w->upload(Tinv);
+    int8_t* H_dev = w->upload(H);
+    w->freq = w->upload(freq);
+    w->idx = w->alloc<int64_t>((size_t)w->nfact * w->N);
+    w->inv_idx = w->alloc<int64_t>((size_t)w->nfact * w->N);
+    CUDA_OK(launch_wreath_index(n, (int)w->N, (int)w->nH, T_dev, Tinv_dev, H_dev, w->idx, w->inv_idx, nullptr));
+    // ---- workspace ----
+    w->Fre = w->alloc<double>((size_t)w->nfact * w->N);
+    w->Fim = w->alloc<double>((size_t)w->nfact * w->N);
+    w->G = w->alloc<double>((size_t)w->nfact * w->N);
+    w->P = w->alloc<double>((size_t)w->N * w->N * bb);
+    CUDA_OK(cudaDeviceSynchronize());
+  });
+  if (rc != SNFFT_OK) {
+    if (w) snfft_wreath_destroy(w);
+    return rc;
+  }
+  *out = w;
+  return SNFFT_OK;
+}
+
+int snfft_wreath_destroy(snfft_wreath* w) {
+  if (!w) return SNFFT_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (w->device >= 0) cudaSetDevice(w->device);
+  for (void* p : w->allocs) cudaFree(p);
+  for (snfft_plan* p : w->factor_plans) snfft_plan_destroy(p);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete w;
+  return SNFFT_OK;
+}
+
+int snfft_wreath_dims(const snfft_wreath* w, int64_t* dims) {
+  return guarded([&] {
+    if (!w || !dims) throw InvalidArg("null argument");
+    dims[0] = w->D;
+    dims[1] = w->N;
+    dims[2] = w->block;
+    dims[3] = w->nH;
+    dims[4] = w->nfact;
+    dims[5] = w->n_ori;
+  });
+}
+
+int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_dev, double* out_im_dev, void* stream_) {
+  return guarded([&] {
+    if (!w || !f_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null argument");
+    DeviceGuard guard(w->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(w->mu);
+    const int64_t bb = w->block * w->block, pairs = w->N * w->N;
+    // stage 1: character sums over the orientations, F_i(sigma) (one pass over f)
+    CUDA_OK(launch_c3_dft(w->m, f_dev, nullptr, w->freq, (int)w->N, w->nfact, w->Fre, w->Fim, false, stream));
+    // stage 2: per coset pair the sum over the Young subgroup: gather by sigma = t_i h t_j^-1, then one GEMM
+    for (int plane = 0; plane < 2; ++plane) {
+      CUDA_OK(launch_gather(plane ? w->Fim : w->Fre, w->idx, w->G, pairs * w->nH, 1, stream));
+      CUDA_OK(launch_dgemm(w->G, w->R, w->P, (int)pairs, (int)bb, (int)w->nH, stream));
+      CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, plane ? out_im_dev : out_re_dev, w->P, 1.0, true, stream));
+    }
+  });
+}
+
+int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const double* fhat_im_dev, double* out_re_dev,
+                         double* out_im_dev, void* stream_) {
+  return guarded([&] {
+    if (!w || !fhat_re_dev || !fhat_im_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null argument");
+    DeviceGuard guard(w->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(w->mu);
+    const int64_t bb = w->block * w->block, pairs = w->N * w->N;
+    for (int plane = 0; plane < 2; ++plane) {
+      CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, const_cast<double*>(plane ? fhat_im_dev : fhat_re_dev), w->P,
+                                    1.0, false, stream));
+      CUDA_OK(launch_dgemm(w->P, w->RT, w->G, (int)pairs, (int)w->nH, (int)bb, stream));  // [pairs][nH]
+      CUDA_OK(launch_gather(w->G, w->inv_idx, plane ? w->Fim : w->Fre, w->nfact * w->N, 1, stream));
+    }
+    CUDA_OK(launch_c3_dft(w->m, w->Fre, w->Fim, w->freq, (int)w->N, w->nfact, out_re_dev, out_im_dev, true, stream));
+    // d tr(rho(g)^H f_hat) / |G| (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140)
+    CUDA_OK(launch_scale2(out_re_dev, out_im_dev, w->nfact * w->n_ori, (double)w->D / ((double)w->nfact * (double)w->n_ori), stream));
   });
 }
 

@@ -1563,6 +1563,61 @@ dgemm_pipe_kernel(const double* __restrict__ A, const double* __restrict__ B, do
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// wreath plan tables and layout kernels (snfft_wreath_*): the gather index sigma = t_i h t_j^-1 of
+// every (coset pair, Young-subgroup element), its inverse, and the block <-> matrix permutes.
+// ---------------------------------------------------------------------------------------------
+__global__ void wreath_index_kernel(int n, int N, int nH, const int8_t* __restrict__ T,
+                                    const int8_t* __restrict__ Tinv, const int8_t* __restrict__ H,
+                                    int64_t* __restrict__ idx, int64_t* __restrict__ inv_idx) {
+  const int64_t total = (int64_t)N * N * nH;
+  int64_t fact[kMaxN + 1];
+  fact[0] = 1;
+  for (int i = 1; i <= kMaxN; ++i) fact[i] = fact[i - 1] * i;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(e % nH);
+    const int j = (int)((e / nH) % N);
+    const int i = (int)(e / ((int64_t)nH * N));
+    int sig[kMaxN];
+    for (int p = 0; p < n; ++p) sig[p] = T[i * n + H[h * n + Tinv[j * n + p] - 1] - 1];  // t_i(h(t_j^-1(p)))
+    int64_t rank = 0;
+    for (int a = 0; a < n; ++a) {
+      int smaller = 0;
+      for (int b = a + 1; b < n; ++b) smaller += sig[b] < sig[a];
+      rank += smaller * fact[n - 1 - a];
+    }
+    const int64_t at = rank * N + i;   // F[sigma][i]
+    idx[e] = at;
+    inv_idx[at] = e;
+  }
+}
+
+// planes [N*N][b*b] (coset pair major) <-> matrix [N*b][N*b]
+template <bool TO_MATRIX>
+__global__ void wreath_permute_kernel(int N, int b, double* __restrict__ mat, double* __restrict__ planes, double scale) {
+  const int64_t D = (int64_t)N * b, total = D * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / D, col = e - row * D;
+    const int64_t i = row / b, a = row - i * b, j = col / b, c = col - j * b;
+    const int64_t q = (i * N + j) * b * b + a * b + c;
+    if (TO_MATRIX) mat[e] = planes[q] * scale; else planes[q] = mat[e] * scale;
+  }
+}
+
+__global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    out[c * rows + r] = in[e];
+  }
+}
+
+__global__ void scale2_kernel(double* __restrict__ a, double* __restrict__ b, int64_t count, double scale) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    a[e] *= scale;
+    b[e] *= scale;
+  }
+}
+
 __global__ void gather_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx,
                               double* __restrict__ dst, int64_t count, int width) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count * width;
@@ -1942,6 +1997,43 @@ cudaError_t launch_inverse_at(int n, const InvAtItem* items, int nitems, const I
   dim3 grid((unsigned)nitems, (unsigned)count);
   LaunchScope scope(kKindYor, stream);
   inverse_at_kernel<<<grid, kThreads, smem_bytes, stream>>>(n, items, irreps, fhat, perms, out);
+  return cudaGetLastError();
+}
+
+static unsigned grid_for(int64_t total) {
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+cudaError_t launch_wreath_index(int n, int N, int nH, const int8_t* T, const int8_t* Tinv, const int8_t* H,
+                                int64_t* idx, int64_t* inv_idx, cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  wreath_index_kernel<<<grid_for((int64_t)N * N * nH), 256, 0, stream>>>(n, N, nH, T, Tinv, H, idx, inv_idx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, double scale, bool to_matrix,
+                                  cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  const int64_t D = (int64_t)N * b;
+  if (to_matrix)
+    wreath_permute_kernel<true><<<grid_for(D * D), 256, 0, stream>>>(N, b, mat, planes, scale);
+  else
+    wreath_permute_kernel<false><<<grid_for(D * D), 256, 0, stream>>>(N, b, mat, planes, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  transpose_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(in, out, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  scale2_kernel<<<grid_for(count), 256, 0, stream>>>(a, b, count, scale);
   return cudaGetLastError();
 }
 

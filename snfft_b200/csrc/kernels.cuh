@@ -68,6 +68,14 @@ cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int
 cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
                           int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream);
 
+// tables and layout helpers of the wreath plan (capi.cu: snfft_wreath_*)
+cudaError_t launch_wreath_index(int n, int N, int nH, const int8_t* T, const int8_t* Tinv, const int8_t* H,
+                                int64_t* idx, int64_t* inv_idx, cudaStream_t stream);
+cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, double scale, bool to_matrix,
+                                  cudaStream_t stream);
+cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream);
+cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cudaStream_t stream);
+
 // dst[e][0..width) = src[idx[e]][0..width)
 cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,
                           cudaStream_t stream);

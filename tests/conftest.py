@@ -1,6 +1,11 @@
 import os
 import sys
 
+# test_gpu_sharded runs all ranks of a virtual world on ONE device, one stream per rank, with
+# device-side barriers between them: the ranks' streams must map to distinct hardware queues or a
+# spinning barrier kernel serialises the rank it waits for (default: 8 queues for 32 pool streams).
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,13 +1,10 @@
 cd $GRAFT_REPO_ROOT
-L=gpurun_out/r2_misc2.log
+L=gpurun_out/r2_misc3.log
 : > $L
-timeout 200 python tools/gemm_bench.py >> $L 2>&1
-timeout 200 python tools/level_step.py 12 1 5 >> $L 2>&1
-SNFFT_WINDOWS="11:7,10/10:7,9" timeout 200 python tools/level_step.py 12 1 5 >> $L 2>&1
-SNFFT_PHASE_A=2 timeout 200 python tools/level_step.py 12 1 5 >> $L 2>&1
-timeout 120 python tools/level_step.py 11 1 5 >> $L 2>&1
-timeout 120 python tools/level_step.py 10 8 5 >> $L 2>&1
-timeout 120 python tools/level_step.py 9 64 5 >> $L 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none --csv --log-file gpurun_out/r2_l12_v53.csv python tools/level_step.py 12 1 1 > gpurun_out/ncu_l12.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:dgemm_pipe -c 1 -o gpurun_out/r2_dgemm python tools/gemm_bench.py > gpurun_out/ncu_full.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 >> $L
+timeout 200 python tools/chunk_sweep.py >> $L 2>&1
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err
+echo "bench rc=$?" >> $L
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_ref.json 2>> gpurun_out/r2_bench_b.err
+echo "ref rc=$?" >> $L
 cat $L
