@@ -202,3 +202,62 @@ def test_pyraminx_group_c2_wr_sn():
             dims += wp.D ** 2
     assert dims == 24 * 16
     assert abs(total - 24 * 16 * (f ** 2).sum()) / total < 1e-12
+
+
+def _c_wreath(alpha, parts, n, all_orientations=0):
+    import ctypes as C
+    from snfft_b200 import _native as N
+    a = np.array(alpha, dtype=np.int32)
+    p = np.zeros((3, n), dtype=np.int32)
+    for k, part in enumerate(parts):
+        p[k, :len(part)] = part
+    h = C.c_void_p()
+    N.check(N.lib.snfft_wreath_create(n, N.ptr(a), N.ptr(p), all_orientations, 0, C.byref(h)))
+    dims = np.zeros(6, dtype=np.int64)
+    N.check(N.lib.snfft_wreath_dims(h, N.ptr(dims)))
+    return h, [int(v) for v in dims]
+
+
+def test_c_abi_wreath_plan_without_the_python_classes():
+    """snfft_wreath_create / _forward / _inverse driven through ctypes alone: the C
+    library builds coset representatives, characters, Young-subgroup matrices and the gather index
+    itself.  Against the oracle on C3 wr S5, against WreathPlan on the cube group."""
+    import ctypes as C
+    from snfft_b200 import _native as N
+    for ci, (alpha, parts) in enumerate(CASES):
+        n = sum(alpha)
+        oris = W.orientations(n)
+        f = np.random.default_rng(500 + ci).standard_normal((math.factorial(n), len(oris)))
+        h, dims = _c_wreath(alpha, parts, n)
+        D = dims[0]
+        assert dims[4] == math.factorial(n) and dims[5] == len(oris)
+        fd = torch.from_numpy(f).cuda()
+        re, im = torch.empty((D, D), dtype=torch.float64, device='cuda'), torch.empty((D, D), dtype=torch.float64, device='cuda')
+        N.check(N.lib.snfft_wreath_forward(h, N.ptr(fd), N.ptr(re), N.ptr(im), None))
+        got = torch.complex(re, im).cpu().numpy()
+        ref = W.wreath_ft_direct(alpha, parts, f, oris)
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10
+        ore, oim = torch.empty_like(fd), torch.empty_like(fd)
+        N.check(N.lib.snfft_wreath_inverse(h, N.ptr(re), N.ptr(im), N.ptr(ore), N.ptr(oim), None))
+        want = W.wreath_inverse_direct(alpha, parts, ref, oris, math.factorial(n) * len(oris))
+        inv = torch.complex(ore, oim).cpu().numpy()
+        assert np.abs(inv - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+        N.check(N.lib.snfft_wreath_destroy(h))
+    # the cube group: same numbers as the Python plan (same kernels underneath, tables built in C++)
+    for alpha, parts in [((2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))), ((8, 0, 0), ((7, 1), (), ())), ((0, 1, 7), ((), (1,), (4, 3)))]:
+        f = torch.randn((40320, 2187), dtype=torch.float64, device='cuda',
+                        generator=torch.Generator(device='cuda').manual_seed(77))
+        h, dims = _c_wreath(alpha, parts, 8)
+        D = dims[0]
+        re, im = torch.empty((D, D), dtype=torch.float64, device='cuda'), torch.empty((D, D), dtype=torch.float64, device='cuda')
+        N.check(N.lib.snfft_wreath_forward(h, N.ptr(f), N.ptr(re), N.ptr(im), None))
+        want = WreathPlan(alpha, parts).forward(f)
+        got = torch.complex(re, im)
+        assert ((got - want).abs().max() / want.abs().max()).item() < 1e-12
+        N.check(N.lib.snfft_wreath_destroy(h))
+        del f, re, im, want, got
+        torch.cuda.empty_cache()
+    # bad arguments come back as statuses, not crashes
+    bad = np.array([1, 1, 1], dtype=np.int32)
+    assert N.lib.snfft_wreath_create(5, N.ptr(bad), N.ptr(np.zeros((3, 5), dtype=np.int32)), 0, 0,
+                                     C.byref(C.c_void_p())) == 1
