@@ -212,12 +212,12 @@ def run_coset_split(n, rank, world, local, steps, warmup, barrier, peak):
     def forward(x):
         if world == 1:
             return plan.forward(x, 'coset', out=spec_buf, work=work)
-        return sp.forward_c(x, sp._p2p['wsk'], out=spec_buf) if sp._p2p else sp.forward(x)
+        return sp.forward_c(x, sp._p2p['wsk'], out=spec_buf) if getattr(sp, '_p2p', None) else sp.forward(x)
 
     def inverse(spec):
         if world == 1:
             return plan.inverse(spec, 'coset', out=back_buf, work=work)
-        return sp.inverse_c(spec, sp._p2p['wsk'], out=back_buf) if sp._p2p else sp.inverse(spec)
+        return sp.inverse_c(spec, sp._p2p['wsk'], out=back_buf) if getattr(sp, '_p2p', None) else sp.inverse(spec)
 
     # ---- parity: f = sum_j c_j delta_{sigma_j}  =>  f_hat(lambda)[:, col] = sum_j c_j rho_lambda(sigma_j)[:, col]
     perms, coefs = PT.sparse_support(n, count=4, seed=1000 + n)
@@ -268,7 +268,7 @@ def run_coset_split(n, rank, world, local, steps, warmup, barrier, peak):
     kinds = timing_read()
     timing_enable(False)
     launches = launch_count() - launches0
-    timed_out = bool(sp is not None and sp._p2p and sp.barrier_timed_out())
+    timed_out = bool(sp is not None and getattr(sp, '_p2p', None) and sp.barrier_timed_out())
     per_kind = {k: round(v[0] / steps, 4) for k, v in kinds.items() if v[1]}
 
     block = {

@@ -326,7 +326,8 @@ int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_bloc
  * pack}; groups int64[..][4] = {first word of the blob, words, rows, rows that stay on the x side
  * (they come first)}; blob_fwd / blob_inv: the program blobs (16 x words bytes each).  A blob is
  * u32 xoff[rows], u32 dest[rows], padding to 16 bytes, then per block a 16-byte header {u16 byte
- * offset (row index * 256) of its rows [5], u16 m, u32 0} followed by the m x m matrix (doubles,
+ * offset (row index * 256) of its rows [5], u16 m, u32 pair flag (1: the next block is of the same
+ * stage and size, the kernel interleaves the two)} followed by the m x m matrix (doubles,
  * row-major, y = C x in place on the rows; padded to 16 bytes), terminated by a header with m = 0;
  * the inverse blob lists the blocks backwards with the inverse matrices. */
 int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes, int32_t* panels,

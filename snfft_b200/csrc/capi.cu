@@ -273,6 +273,7 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, Uploader
         for (int dir = 0; dir < 2; ++dir) {
           std::vector<U128>& out = dir ? blob_i : blob_f;
           push_words(out, table.data(), table.size() * sizeof(uint32_t));
+          bool paired = false;  // the previous block announced this one as its partner
           for (uint32_t bq = 0; bq < G.nblk; ++bq) {
             // forward: stage order; inverse: the same blocks backwards with the inverse matrices
             const PhaseBlock& pb = pp.blocks[G.blk_off + (dir ? G.nblk - 1 - bq : bq)];
@@ -283,7 +284,14 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, Uploader
             h.x = off[0] | ((uint32_t)off[1] << 16);
             h.y = off[2] | ((uint32_t)off[3] << 16);
             h.z = off[4] | ((uint32_t)pb.m << 16);
+            // pair flag: the next block belongs to the same stage (blocks of a stage touch disjoint
+            // rows) and has the same size <= 3: the kernel runs the two interleaved
             h.w = 0;
+            if (!paired && bq + 1 < G.nblk && pb.m <= 3) {
+              const PhaseBlock& nx = pp.blocks[G.blk_off + (dir ? G.nblk - 2 - bq : bq + 1)];
+              if (nx.stage == pb.stage && nx.m == pb.m) h.w = 1;
+            }
+            paired = h.w != 0;
             out.push_back(h);
             push_words(out, &prog.coef[dir ? pb.coef_i : pb.coef_f], (size_t)pb.m * pb.m * sizeof(double));
           }

@@ -47,7 +47,7 @@ struct Tile {
 // the group's blocks as a byte stream that a warp copies into shared memory and then interprets
 // for many column chunks - no pointer chasing and no table decoding in the inner loop.
 //   blob = u32 xoff[nrows], u32 dest[nrows] (padded to 16 bytes), then per block
-//          a 16-byte header {u16 byte offset of its m rows in the warp's tile [5]; u16 m; u32 0}
+//          a 16-byte header {u16 byte offset of its m rows in the warp's tile [5]; u16 m; u32 pair flag}
 //          followed by the m x m matrix (doubles, row-major out x in, padded to 16 bytes),
 //          terminated by a header with m = 0.
 // Rows that stay on the x side come first, rows finished in this phase last.

@@ -854,6 +854,54 @@ __device__ __forceinline__ void stream_block(unsigned pc, const U128 h, unsigned
     for (int a = 0; a < M; ++a) sts_f64(row[a] + 256u * q, y[q][a]);
 }
 
+// two blocks of one stage (disjoint rows, equal size) interleaved: twice the independent work per
+// warp between the shared-memory round trips (the host marks such pairs in the header, M <= 3)
+template <int M, int A>
+__device__ __forceinline__ void stream_block_pair(unsigned pc0, const U128 h0, unsigned pc1, const U128 h1, unsigned col) {
+  double cm[2][M * M + 1];
+#pragma unroll
+  for (int i = 0; i < (M * M + 1) / 2; ++i) {
+    double a, b;
+    lds_f64x2(pc0 + 16u + 16u * i, a, b);
+    cm[0][2 * i] = a;
+    if (2 * i + 1 < M * M + 1) cm[0][2 * i + 1] = b;
+    lds_f64x2(pc1 + 16u + 16u * i, a, b);
+    cm[1][2 * i] = a;
+    if (2 * i + 1 < M * M + 1) cm[1][2 * i + 1] = b;
+  }
+  unsigned row[2][3];
+  row[0][0] = col + (h0.x & 0xffffu) * A;
+  row[0][1] = col + (h0.x >> 16) * A;
+  row[0][2] = col + (h0.y & 0xffffu) * A;
+  row[1][0] = col + (h1.x & 0xffffu) * A;
+  row[1][1] = col + (h1.x >> 16) * A;
+  row[1][2] = col + (h1.y & 0xffffu) * A;
+  double x[2][A][M], y[2][A][M];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < A; ++q)
+#pragma unroll
+      for (int b = 0; b < M; ++b) x[p][q][b] = lds_f64(row[p][b] + 256u * q);
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < A; ++q)
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double acc = cm[p][a * M] * x[p][q][0];
+#pragma unroll
+        for (int b = 1; b < M; ++b) acc = fma(cm[p][a * M + b], x[p][q][b], acc);
+        y[p][q][a] = acc;
+      }
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < A; ++q)
+#pragma unroll
+      for (int a = 0; a < M; ++a) sts_f64(row[p][a] + 256u * q, y[p][q][a]);
+}
+
 // A = chunks of 32 columns a warp runs side by side (one read of every header and matrix for both)
 template <bool INV, int A>
 __global__ void __launch_bounds__(512, 1)
@@ -953,8 +1001,20 @@ phase_kernel(PhaseDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __r
       while (true) {
         const uint32_t m = h.z >> 16;
         if (m == 0) break;
-        const unsigned next = pc + 16u + 16u * ((m * m + 1) >> 1);
+        const unsigned len = 16u + 16u * ((m * m + 1) >> 1);
+        const unsigned next = pc + len;
         const U128 hn = lds_u128(next);
+        if (h.w != 0 && A <= 2) {  // this block and the next one: same stage, same size (2 or 3), disjoint rows
+          const unsigned next2 = next + len;
+          const U128 hn2 = lds_u128(next2);
+          if (m == 2)
+            stream_block_pair<2, A <= 2 ? A : 1>(pc, h, next, hn, tile_s);
+          else
+            stream_block_pair<3, A <= 2 ? A : 1>(pc, h, next, hn, tile_s);
+          pc = next2;
+          h = hn2;
+          continue;
+        }
         switch (m) {
           case 2: stream_block<2, A>(pc, h, tile_s); break;
           case 3: stream_block<3, A>(pc, h, tile_s); break;

@@ -50,6 +50,7 @@ class ShardedPlan:
             self.block_range.append((b.value, e.value))
         self.sizes = [[self._size(r, k) for k in range(n + 1)] for r in range(world)]
         self._idx = {}
+        self._p2p = None        # set by enable_p2p(): the peer-memory workspace of the C schedule
 
     def close(self):
         if getattr(self, '_h', None):
