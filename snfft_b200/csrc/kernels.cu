@@ -1335,8 +1335,49 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
 // radix-3 passes run in place, and only the N needed frequencies are written.  INV: the adjoint -
 // the N values are scattered onto the frequency grid and the conjugate DFT gives all 3^m values.
 // ---------------------------------------------------------------------------------------------
+// D consecutive base-3 digits (strides s, 3s, .. of the grid) transformed in registers: a 3^D-point
+// DFT per thread, D radix-3 stages on compile-time indices, one shared-memory round trip
+template <int D, bool INV>
+__device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __restrict__ im, int base, int s) {
+  constexpr int P = D == 1 ? 3 : (D == 2 ? 9 : 27);
+  const double h = INV ? -0.8660254037844386467637231707529 : 0.8660254037844386467637231707529;  // +-sqrt(3)/2
+  double xr[P], xi[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    xr[j] = re[base + j * s];
+    xi[j] = im[base + j * s];
+  }
+#pragma unroll
+  for (int dg = 0; dg < D; ++dg) {
+    const int st = dg == 0 ? 1 : (dg == 1 ? 3 : 9);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if ((j / st) % 3 != 0) continue;  // j = index with digit dg equal to 0
+      const double x0r = xr[j], x0i = xi[j];
+      const double x1r = xr[j + st], x1i = xi[j + st];
+      const double x2r = xr[j + 2 * st], x2i = xi[j + 2 * st];
+      const double sr = x1r + x2r, si = x1i + x2i;
+      const double dr = (x1r - x2r) * h, di = (x1i - x2i) * h;
+      xr[j] = x0r + sr;
+      xi[j] = x0i + si;
+      // X_1 = x0 - (x1 + x2)/2 + i (x1 - x2) sqrt(3)/2 ; X_2 = its mirror (signs flipped for the adjoint)
+      xr[j + st] = x0r - 0.5 * sr - di;
+      xi[j + st] = x0i - 0.5 * si + dr;
+      xr[j + 2 * st] = x0r - 0.5 * sr + di;
+      xi[j + 2 * st] = x0i - 0.5 * si - dr;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    re[base + j * s] = xr[j];
+    im[base + j * s] = xi[j];
+  }
+}
+
+constexpr int kDftThreads = 128;
+
 template <bool INV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kDftThreads)
 c3_dft_kernel(int m, int size, const double* __restrict__ in_re, const double* __restrict__ in_im,
               const int32_t* __restrict__ freq, int nfreq, double* __restrict__ out_re,
               double* __restrict__ out_im) {
@@ -1345,48 +1386,45 @@ c3_dft_kernel(int m, int size, const double* __restrict__ in_re, const double* _
   double* im = grid + size;
   const int64_t sig = blockIdx.x;
   if (!INV) {
-    for (int e = threadIdx.x; e < size; e += kThreads) {
+    for (int e = threadIdx.x; e < size; e += kDftThreads) {
       re[e] = in_re[sig * size + e];
       im[e] = 0.0;
     }
   } else {
-    for (int e = threadIdx.x; e < size; e += kThreads) re[e] = im[e] = 0.0;
+    for (int e = threadIdx.x; e < size; e += kDftThreads) re[e] = im[e] = 0.0;
     __syncthreads();
-    for (int i = threadIdx.x; i < nfreq; i += kThreads) {
+    for (int i = threadIdx.x; i < nfreq; i += kDftThreads) {
       re[freq[i]] = in_re[sig * nfreq + i];
       im[freq[i]] = in_im[sig * nfreq + i];
     }
   }
   __syncthreads();
-  const double h = 0.8660254037844386467637231707529;  // sqrt(3) / 2
-  const double sgn = INV ? -1.0 : 1.0;                  // forward: omega^{+k o}; adjoint: omega^{-k o}
-  int stride = 1;
-  for (int a = 0; a < m; ++a, stride *= 3) {
-    for (int t = threadIdx.x; t < size / 3; t += kThreads) {
+  // forward: omega^{+k o}; adjoint: omega^{-k o}.  Two digits per pass (9 points per thread in
+  // registers: 243 independent sub-transforms per pass for the 2x2 cube, ~80 registers), then the
+  // odd digit: 4 barriers instead of 7
+  int done = 0, stride = 1;
+  while (done < m) {
+    const int dg = m - done >= 2 ? 2 : 1;
+    const int pts = dg == 2 ? 9 : 3;
+    for (int t = threadIdx.x; t < size / pts; t += kDftThreads) {
       const int hi = t / stride, lo = t - hi * stride;
-      const int base = hi * 3 * stride + lo;
-      const double x0r = re[base], x0i = im[base];
-      const double x1r = re[base + stride], x1i = im[base + stride];
-      const double x2r = re[base + 2 * stride], x2i = im[base + 2 * stride];
-      const double sr = x1r + x2r, si = x1i + x2i;          // x1 + x2
-      const double dr = (x1r - x2r) * h * sgn, di = (x1i - x2i) * h * sgn;  // (x1 - x2) * (+-sqrt(3)/2)
-      re[base] = x0r + sr;
-      im[base] = x0i + si;
-      // X_1 = x0 - (x1 + x2)/2 + i (x1 - x2) sqrt(3)/2 ; X_2 = x0 - (x1 + x2)/2 - i (x1 - x2) sqrt(3)/2
-      re[base + stride] = x0r - 0.5 * sr - di;
-      im[base + stride] = x0i - 0.5 * si + dr;
-      re[base + 2 * stride] = x0r - 0.5 * sr + di;
-      im[base + 2 * stride] = x0i - 0.5 * si - dr;
+      const int base = hi * pts * stride + lo;
+      if (dg == 2)
+        c3_digits<2, INV>(re, im, base, stride);
+      else
+        c3_digits<1, INV>(re, im, base, stride);
     }
     __syncthreads();
+    done += dg;
+    stride *= pts;
   }
   if (!INV) {
-    for (int i = threadIdx.x; i < nfreq; i += kThreads) {
+    for (int i = threadIdx.x; i < nfreq; i += kDftThreads) {
       out_re[sig * nfreq + i] = re[freq[i]];
       out_im[sig * nfreq + i] = im[freq[i]];
     }
   } else {
-    for (int e = threadIdx.x; e < size; e += kThreads) {
+    for (int e = threadIdx.x; e < size; e += kDftThreads) {
       out_re[sig * size + e] = re[e];
       out_im[sig * size + e] = im[e];
     }
@@ -2106,9 +2144,9 @@ cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const
   const size_t smem = 2 * (size_t)size * sizeof(double);
   LaunchScope scope(kKindOther, stream);
   if (inverse)
-    c3_dft_kernel<true><<<(unsigned)count, kThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+    c3_dft_kernel<true><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
   else
-    c3_dft_kernel<false><<<(unsigned)count, kThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+    c3_dft_kernel<false><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
   return cudaGetLastError();
 }
 

@@ -277,8 +277,7 @@ class WreathPlan:
         self.alpha, self.parts, self.device = tuple(alpha), tuple(tuple(p) for p in parts), device
         self.n = n = sum(alpha)
         dev = f'cuda:{device}'
-        tabs = _alpha_tables(self.alpha, device)
-        self.reps = tabs['reps']
+        self.reps = young_coset_reps(self.alpha)
         self.N = len(self.reps)
         self.block = wreath_dim(self.parts)
         self.D = self.N * self.block
@@ -292,6 +291,25 @@ class WreathPlan:
         self.order = math.factorial(n) * len(self.oris)
         self.mode = orientation_mode(self.oris, n) if m == 3 else None
         self.seg = np.repeat(np.arange(m), self.alpha)               # segment of position p
+        self._c = None
+        if self.mode is not None and n <= 9:
+            # the standard C_3 layouts: the whole transform lives behind the C ABI (tables built in
+            # C++ / on the device); this class is a thin caller
+            a = np.array(self.alpha, dtype=np.int32)
+            pz = np.zeros((3, n), dtype=np.int32)
+            for k, part in enumerate(self.parts):
+                pz[k, :len(part)] = part
+            handle = C.c_void_p()
+            N.check(N.lib.snfft_wreath_create(n, N.ptr(a), N.ptr(pz), int(self.mode == 'full'), device,
+                                              C.byref(handle)))
+            self._c = handle
+            dims = np.zeros(6, dtype=np.int64)
+            N.check(N.lib.snfft_wreath_dims(self._c, N.ptr(dims)))
+            assert (int(dims[0]), int(dims[1]), int(dims[2])) == (self.D, self.N, self.block)
+            self.nH = int(dims[3])
+            self.dft_m = n if self.mode == 'full' else n - 1
+            return
+        tabs = _alpha_tables(self.alpha, device)
         T = tabs['T']
         if self.mode is not None:
             self.dft_m = n if self.mode == 'full' else n - 1
@@ -327,6 +345,35 @@ class WreathPlan:
         # sigma = t_i h t_j^-1 for every (i, j, h): one gather index into F[sigma][i]
         self.idx, self.inv_idx = tabs['idx'], tabs['inv_idx']
 
+    def close(self):
+        if getattr(self, '_c', None):
+            N.lib.snfft_wreath_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _tables(self):
+        """R (Young-subgroup matrices) and the coset tables for the host-side helpers of a plan that
+        runs behind the C ABI (``inverse_at``)."""
+        import torch
+        if getattr(self, 'R', None) is None:
+            dev = f'cuda:{self.device}'
+            R = None
+            for ak, pk in zip(self.alpha, self.parts):
+                if ak == 0:
+                    continue
+                plan = get_plan(ak, self.device)
+                perms = torch.tensor(list(itertools.permutations(range(1, ak + 1))), dtype=torch.int32, device=dev)
+                mats = plan.yor(plan.irrep_index(pk), perms)
+                R = mats if R is None else torch.einsum('xab,ycd->xyacbd', R, mats).reshape(
+                    R.shape[0] * mats.shape[0], R.shape[1] * mats.shape[1], R.shape[2] * mats.shape[2])
+            self.R = R.reshape(R.shape[0], self.block * self.block).contiguous()
+        return self.R
+
     # -- thin wrappers over the C ABI
     def _gemm(self, a, b):
         import torch
@@ -359,6 +406,9 @@ class WreathPlan:
     def character_sums(self, f):
         """Stage 1: (re, im) of F_i(sigma) = sum_o f(sigma, o) chi_i(o), each [n!, N]."""
         if self.mode is not None:
+            if getattr(self, 'freq', None) is None:
+                import torch
+                self.freq = torch.from_numpy(dft_frequencies(self.alpha, self.reps, self.mode)).to(f.device)
             return self._dft(f, None, False)
         return self._gemm(f, self.Xre), self._gemm(f, self.Xim)
 
@@ -368,6 +418,13 @@ class WreathPlan:
         if f.dtype != torch.float64 or not f.is_cuda or tuple(f.shape) != (math.factorial(self.n), len(self.oris)):
             raise TypeError('f must be a float64 CUDA tensor [n!, n_orientations]')
         f = f.contiguous()
+        if self._c is not None:
+            re = torch.empty((self.D, self.D), dtype=torch.float64, device=f.device)
+            im = torch.empty((self.D, self.D), dtype=torch.float64, device=f.device)
+            with torch.cuda.device(self.device):
+                N.check(N.lib.snfft_wreath_forward(self._c, N.ptr(f), N.ptr(re), N.ptr(im),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return torch.complex(re, im)
         with torch.cuda.device(self.device):
             planes = []
             for F in self.character_sums(f):                          # [n!, N]
@@ -380,6 +437,15 @@ class WreathPlan:
         """complex128 [n!, n_ori]: D tr(rho(g)^H f_hat) / |G| at every group element
         (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140)."""
         import torch
+        if self._c is not None:
+            fre, fim = fhat.real.contiguous(), fhat.imag.contiguous()
+            shape = (math.factorial(self.n), len(self.oris))
+            re = torch.empty(shape, dtype=torch.float64, device=fhat.device)
+            im = torch.empty(shape, dtype=torch.float64, device=fhat.device)
+            with torch.cuda.device(self.device):
+                N.check(N.lib.snfft_wreath_inverse(self._c, N.ptr(fre), N.ptr(fim), N.ptr(re), N.ptr(im),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return torch.complex(re, im)
         B = fhat.reshape(self.N, self.block, self.N, self.block).permute(0, 2, 1, 3).reshape(
             self.N * self.N, self.block * self.block)
         with torch.cuda.device(self.device):
@@ -411,7 +477,7 @@ class WreathPlan:
         Hlist = [p.tup_rep for p in young_subgroup_perm(self.alpha)]
         hindex = {h: q for q, h in enumerate(Hlist)}
         out = []
-        Rm = self.R.reshape(self.nH, b, b)
+        Rm = self._tables().reshape(len(Hlist), b, b)
         for ori, sigma in elements:
             sig = np.array(sigma, dtype=np.int64)
             ii, hh = [], []
