@@ -214,7 +214,8 @@ int snfft_shard_exchange(snfft_shard* shard, const void* const* peer_bufs, void*
  *   status       : device int, zeroed once; set to 1 if a barrier gave up waiting for a peer (~2 s).
  * f_local_dev: this rank's slice of the coset-major function (snfft_shard_blocks x m!, preserved);
  * fhat_compact_dev: snfft_shard_size(rank, n) doubles, the compact spectrum of this rank.
- * Every rank must make the same sequence of sharded calls. */
+ * Every rank must make the same sequence of sharded calls, and one shard object runs one sharded
+ * call at a time (the barrier epochs are counted per shard). */
 typedef struct snfft_shard_ws {
   void* peer_cols[16];
   void* peer_pads[16];
@@ -241,7 +242,8 @@ int snfft_inverse_sharded(snfft_shard* shard, const double* fhat_compact_dev, do
  * index of sigma = t_i h t_j^-1 for every coset pair.  alpha: int32[3], a weak partition of n;
  * parts: int32[3][n], the three partitions zero-padded to n entries; all_orientations = 0: the
  * orientation axis holds the 3^(n-1) tuples with zero sum mod 3 in product order (utils.py:206-209:
- * index = base-3 number of the first n-1 letters), != 0: all 3^n tuples.  n <= 9.
+ * index = base-3 number of the first n-1 letters), != 0: all 3^n tuples.  At most 3^8 orientations
+ * (n <= 9 with zero sum, n <= 8 with all).
  * f_dev: double[n!][orientations], sigma in perm2.sn order (lexicographic).  Output: the complex
  * D x D matrix as two row-major planes (D = cosets x block).  A plan serialises its transforms
  * (one shared workspace).  dims int64[6] = {D, cosets N, block, |S_alpha|, n!, orientations}. */
@@ -268,7 +270,7 @@ int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t
  * significant) is transformed with m radix-3 passes in shared memory and only the nfreq frequencies
  * listed in freq_dev (same indexing) are written: out[count][nfreq] = sum_o in[o] omega^{+k.o}.
  * inverse != 0 is the adjoint: in [count][nfreq] complex is scattered onto the frequency grid and
- * out [count][3^m] = sum_k in[k] omega^{-k.o} (no normalisation).  m <= 9. */
+ * out [count][3^m] = sum_k in[k] omega^{-k.o} (no normalisation).  m <= 8. */
 int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
                  int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream);
 /* dst[e][0..width) = src[idx[e]][0..width) for e < count: regroups S_n by cosets of a Young
@@ -298,7 +300,7 @@ int snfft_debug_fused_tma(int on);
  * events on its stream.  snfft_timing_read synchronises them, fills ms_by_kind[15] and
  * launches_by_kind[15] and resets the totals.  Kinds: 0 fused forward (levels 2..7), 1 fused
  * inverse, 2 level 8 forward (generated), 3 level 8 inverse, 4 table-driven level kernel,
- * 5 in-place stages 1..4 of a level >= 9, 6 finished-row move of those levels, 7 row-group phase
+ * 5 in-place stages 1..5 of a level >= 9, 6 finished-row move of those levels, 7 row-group phase
  * forward, 8 row-group phase inverse, 9 peer-memory exchange, 10 device-side barrier between
  * ranks (includes waiting for the slowest rank), 11 reorder, 12 yor, 13 dgemm, 14 other. */
 #define SNFFT_NUM_KERNEL_KINDS 15
@@ -319,7 +321,7 @@ int snfft_export_panel(const snfft_plan* plan, int k, int panel, int32_t* n_bloc
                        int64_t* rowbase);
 
 /* Host-side export of the device tables of one row-group phase of level k >= 9 (phase >= 1; phase 0
- * is stages 1..4, generated programs), so that CPU tests can interpret exactly what the phase
+ * is stages 1..5, generated programs), so that CPU tests can interpret exactly what the phase
  * kernel executes.  sizes int32[8] = {panels, groups, 16-byte words of a blob array, rows of the
  * largest group, words of the largest blob, stages, first stage, phases of the level}; the other
  * buffers may be NULL to query sizes: panels int32[..][5] = {columns, tiles, first group, groups,

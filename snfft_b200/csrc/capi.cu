@@ -80,7 +80,7 @@ struct snfft_plan {
   size_t level_smem[kMaxN + 1] = {};
   FusedDev fused;
   std::vector<PhaseHost> phase_dev[kMaxN + 1];  // row-group phases of levels >= 9
-  P1Dev p1_dev[kMaxN + 1] = {};                // generated in-place stages 1..4 of levels >= 9
+  P1Dev p1_dev[kMaxN + 1] = {};                // generated in-place stages 1..kP1Stages of levels >= 9
   uint32_t* lex_table = nullptr;
   std::mutex lazy_mu;
   std::map<int, YorTables> yor_tables;
@@ -219,7 +219,7 @@ void build_phase_devs(const LevelProgram& prog, const LevelLayout& lay, Uploader
                       std::vector<PhaseHost>& out_devs) {
   if (prog.panels.empty() || prog.panels[0].phases.empty()) return;
   const size_t nphases = prog.panels[0].phases.size();
-  out_devs.push_back(PhaseHost{});  // phase 0 (stages 1..4) runs as generated programs: placeholder
+  out_devs.push_back(PhaseHost{});  // phase 0 (stages 1..kP1Stages) runs as generated programs: placeholder
   for (size_t ph = 1; ph < nphases; ++ph) {
     const int stage_lo = prog.panels[0].phases[ph].stage_lo, stage_hi = prog.panels[0].phases[ph].stage_hi;
     std::vector<PhasePanelDev> panels;
@@ -330,27 +330,36 @@ void build_p1_dev(const LevelProgram& prog, const LevelLayout& lay, Uploader&& u
     for (int cw = 0; cw < P.d; ++cw)
       if (P.chain_base[cw] == cw)
         entries.push_back(P1Entry{P.chain_sigma[cw], w, lay.panel_off[p] + (int64_t)cw * w, 0});
-    // rows whose last writer is a block of stages 1..4
+    // rows whose last writer is a block of stages 1..kP1Stages
     std::vector<int> last(P.k * P.d, -1);
     for (size_t b = 0; b < P.blocks.size(); ++b)
       for (int a = 0; a < P.blocks[b].m; ++a) last[P.blocks[b].slot[a]] = (int)b;
     for (int s = 0; s < P.k * P.d; ++s)
-      if (last[s] < 4 * P.d)
+      if (last[s] < kP1Stages * P.d)
         rows.push_back(P0Row{lay.rowbase[p][s], lay.dest[p][s], w, 0, P.fscale[s], P.fscale[s] * P.weight[s], 0});
   }
   std::stable_sort(entries.begin(), entries.end(), [](const P1Entry& a, const P1Entry& b) { return a.sigma < b.sigma; });
   int64_t items = 0;
-  for (P1Entry& e : entries) {
+  std::vector<uint32_t> item_entry, item_row;
+  for (size_t i = 0; i < entries.size(); ++i) {
+    P1Entry& e = entries[i];
     e.item_off = items;
-    items += (e.d + 31) / 32;
+    const int tiles = (e.d + 31) / 32;
+    items += tiles;
+    item_entry.insert(item_entry.end(), (size_t)tiles, (uint32_t)i);
   }
   int64_t row_items = 0;
-  for (P0Row& r : rows) {
+  for (size_t i = 0; i < rows.size(); ++i) {
+    P0Row& r = rows[i];
     r.item_off = row_items;
-    row_items += (r.d + 31) / 32;
+    const int tiles = (r.d + 31) / 32;
+    row_items += tiles;
+    item_row.insert(item_row.end(), (size_t)tiles, (uint32_t)i);
   }
   D.entries = up(entries);
   D.rows = up(rows);
+  D.item_entry = up(item_entry);
+  D.item_row = up(item_row);
   D.nitems = items;
   D.nrow_items = row_items;
   D.in_stride = lay.in_stride;
@@ -455,7 +464,7 @@ void run_level_phases(const snfft_plan* plan, int k, double* xside, double* ssid
 void run_phases(const std::vector<PhaseHost>& phases, const P1Dev& p1, int num_sms, double* xside,
                 double* sside, int64_t groups, bool inverse, cudaStream_t stream) {
   const int np = (int)phases.size();
-  // phase 0 (stages 1..4) runs as generated in-place register programs, the others table-driven
+  // phase 0 (stages 1..kP1Stages) runs as generated in-place register programs, the others interpreted
   if (!inverse) CUDA_OK(launch_p1_inplace(p1, xside, sside, groups, false, num_sms, stream));
   for (int i = 1; i < np; ++i)
   {
@@ -647,7 +656,7 @@ void build_shard_level(snfft_shard* sh, int k) {
 
 extern "C" {
 
-int snfft_abi_version(void) { return 1; }
+int snfft_abi_version(void) { return 2; }
 
 const char* snfft_last_error(void) { return g_last_error.c_str(); }
 
@@ -1444,6 +1453,12 @@ struct snfft_wreath {
   int64_t N = 0, nH = 0, block = 0, D = 0, nfact = 0, n_ori = 0;
   int32_t* freq = nullptr;
   int64_t *idx = nullptr, *inv_idx = nullptr;
+  int64_t* idx_t = nullptr;                                // idx transposed to [h][pair] (fused stage 2), or null
+  // alpha = (n, 0, 0) up to order: S_alpha = S_n, one coset, and stage 2 IS the S_n Fourier transform of
+  // the character sum at the irrep `parts`: it runs through the Clausen-Baum levels (forward_impl)
+  snfft_plan* sn_plan = nullptr;
+  int64_t sn_off = 0;
+  double *sn_spec = nullptr, *sn_work = nullptr;
   double *R = nullptr, *RT = nullptr;                      // [nH][b*b] and its transpose
   double *Fre = nullptr, *Fim = nullptr, *G = nullptr, *P = nullptr;  // workspace
   std::vector<void*> allocs;
@@ -1491,6 +1506,7 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     w->device = device;
     w->m = all_orientations ? n : n - 1;
     if (w->m < 1) throw InvalidArg("the zero-sum orientation group of C_3 wr S_1 is trivial");
+    if (w->m > 8) throw InvalidArg("at most 3^8 orientations (the orientation grid lives in shared memory)");
     for (int k = 0; k < 3; ++k) w->alpha[k] = alpha[k];
     w->nfact = 1;
     for (int i = 2; i <= n; ++i) w->nfact *= i;
@@ -1595,6 +1611,10 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
       CUDA_OK(cudaDeviceSynchronize());
       if (nontrivial == 1) {
         single_dev = mats_dev;  // R is this factor's table itself
+        if (a == n && n >= 2) {
+          w->sn_plan = fp;
+          w->sn_off = shapes[irrep].off;
+        }
       } else {
         seg_mats[k].resize((size_t)cnt * d * d);
         CUDA_OK(cudaMemcpy(seg_mats[k].data(), mats_dev, seg_mats[k].size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1651,11 +1671,19 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     w->idx = w->alloc<int64_t>((size_t)w->nfact * w->N);
     w->inv_idx = w->alloc<int64_t>((size_t)w->nfact * w->N);
     CUDA_OK(launch_wreath_index(n, (int)w->N, (int)w->nH, T_dev, Tinv_dev, H_dev, w->idx, w->inv_idx, nullptr));
+    if (wreath_stage2_fits((int)w->N, (int)w->block, (int)w->nH)) {
+      w->idx_t = w->alloc<int64_t>((size_t)w->nfact * w->N);
+      CUDA_OK(launch_transpose_i64(w->idx, w->idx_t, w->N * w->N, w->nH, nullptr));
+    }
     // ---- workspace ----
     w->Fre = w->alloc<double>((size_t)w->nfact * w->N);
     w->Fim = w->alloc<double>((size_t)w->nfact * w->N);
     w->G = w->alloc<double>((size_t)w->nfact * w->N);
     w->P = w->alloc<double>((size_t)w->N * w->N * bb);
+    if (w->sn_plan) {
+      w->sn_spec = w->alloc<double>((size_t)w->nfact);
+      w->sn_work = w->alloc<double>((size_t)w->nfact);
+    }
     CUDA_OK(cudaDeviceSynchronize());
   });
   if (rc != SNFFT_OK) {
@@ -1699,7 +1727,23 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
     const int64_t bb = w->block * w->block, pairs = w->N * w->N;
     // stage 1: character sums over the orientations, F_i(sigma) (one pass over f)
     CUDA_OK(launch_c3_dft(w->m, f_dev, nullptr, w->freq, (int)w->N, w->nfact, w->Fre, w->Fim, false, stream));
-    // stage 2: per coset pair the sum over the Young subgroup: gather by sigma = t_i h t_j^-1, then one GEMM
+    // stage 2: per coset pair the sum over the Young subgroup.  One coset (S_alpha = S_n): the S_n
+    // transform of F itself - the same level recursion as snfft_forward, from lexicographic order -
+    // and the block of the irrep `parts` out of the packed spectrum.  Small blocks: one fused kernel;
+    // otherwise gather by sigma = t_i h t_j^-1, one DMMA GEMM and the block placement per plane
+    if (w->sn_plan) {
+      for (int plane = 0; plane < 2; ++plane) {
+        forward_impl(w->sn_plan, w->n, plane ? w->Fim : w->Fre, w->sn_spec, w->sn_work, 1, true, stream);
+        CUDA_OK(cudaMemcpyAsync(plane ? out_im_dev : out_re_dev, w->sn_spec + w->sn_off, (size_t)bb * sizeof(double),
+                                cudaMemcpyDeviceToDevice, stream));
+      }
+      return;
+    }
+    if (w->idx_t) {
+      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->idx_t, w->R, w->Fre, w->Fim, out_re_dev,
+                                   out_im_dev, false, stream));
+      return;
+    }
     for (int plane = 0; plane < 2; ++plane) {
       CUDA_OK(launch_gather(plane ? w->Fim : w->Fre, w->idx, w->G, pairs * w->nH, 1, stream));
       CUDA_OK(launch_dgemm(w->G, w->R, w->P, (int)pairs, (int)bb, (int)w->nH, stream));
@@ -1716,12 +1760,15 @@ int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const doubl
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lock(w->mu);
     const int64_t bb = w->block * w->block, pairs = w->N * w->N;
-    for (int plane = 0; plane < 2; ++plane) {
+    for (int plane = 0; plane < 2 && !w->idx_t; ++plane) {
       CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, const_cast<double*>(plane ? fhat_im_dev : fhat_re_dev), w->P,
                                     1.0, false, stream));
       CUDA_OK(launch_dgemm(w->P, w->RT, w->G, (int)pairs, (int)w->nH, (int)bb, stream));  // [pairs][nH]
       CUDA_OK(launch_gather(w->G, w->inv_idx, plane ? w->Fim : w->Fre, w->nfact * w->N, 1, stream));
     }
+    if (w->idx_t)
+      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->idx_t, w->R, w->Fre, w->Fim,
+                                   const_cast<double*>(fhat_re_dev), const_cast<double*>(fhat_im_dev), true, stream));
     CUDA_OK(launch_c3_dft(w->m, w->Fre, w->Fim, w->freq, (int)w->N, w->nfact, out_re_dev, out_im_dev, true, stream));
     // d tr(rho(g)^H f_hat) / |G| (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140)
     CUDA_OK(launch_scale2(out_re_dev, out_im_dev, w->nfact * w->n_ori, (double)w->D / ((double)w->nfact * (double)w->n_ori), stream));
@@ -1733,7 +1780,7 @@ int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const 
   return guarded([&] {
     if (!in_re_dev || !freq_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null device buffer");
     if (inverse && !in_im_dev) throw InvalidArg("the adjoint transform needs the imaginary plane");
-    if (m < 1 || m > 9) throw InvalidArg("m must be in 1..9");
+    if (m < 1 || m > 8) throw InvalidArg("m must be in 1..8 (the 3^m grid lives in shared memory)");
     if (nfreq < 1 || count < 0) throw InvalidArg("bad shape");
     ensure_kernels_prepared();
     CUDA_OK(launch_c3_dft(m, in_re_dev, in_im_dev, freq_dev, nfreq, count, out_re_dev, out_im_dev, inverse != 0,
@@ -1757,7 +1804,7 @@ int snfft_export_phase(const snfft_plan* plan, int k, int phase, int32_t* sizes,
     if (k < kPhaseMinLevel || k > plan->host.n) throw InvalidArg("row-group phases exist for levels 9..n");
     const LevelProgram& prog = plan->host.programs[k];
     const int nphases = (int)prog.panels[0].phases.size();
-    if (phase < 1 || phase >= nphases) throw InvalidArg("phase must be in 1..phases-1 (phase 0 = generated stages 1..4)");
+    if (phase < 1 || phase >= nphases) throw InvalidArg("phase must be in 1..phases-1 (phase 0 = the generated stages)");
     // the same builder as the device tables, "uploading" into host memory
     std::vector<std::vector<char>> keep;
     auto up = [&](const auto& v) {

@@ -81,14 +81,14 @@ struct PhaseDev {
 };
 
 // In-place phase 1 of a large level as generated register programs: one entry per (panel, upper
-// chain down to W^5); rows (i, t), i < 5, t < d_sigma at base + i * (k-1)! + t * d.
+// chain down to W^5); rows (i, t), i <= kP1Stages, t < d_sigma at base + i * (k-1)! + t * d.
 struct P1Entry {
   int32_t sigma;     // program (shape of W^5)
   int32_t d;         // columns and row pitch of the panel
   int64_t base;      // in_off + ubase * d
   int64_t item_off;  // prefix sum of ceil(d / 32) over the entries
 };
-// A row that is finished after stage 4: forward out[dest] = scale_f * x[xoff]; inverse
+// A row that is finished after the generated stages (1..kP1Stages): forward out[dest] = scale_f * x[xoff]; inverse
 // x[xoff] = scale_i * out[dest].
 struct P0Row {
   uint32_t xoff, dest;
@@ -100,6 +100,8 @@ struct P0Row {
 struct P1Dev {
   const P1Entry* entries;
   const P0Row* rows;
+  const uint32_t* item_entry;  // item (entry, 32-column tile) -> entry: one table read instead of a binary search
+  const uint32_t* item_row;    // item (finished row, 32-column tile) -> row
   int64_t nitems, nrow_items;
   int64_t in_stride, out_stride;
   int64_t rI;  // (k-1)!

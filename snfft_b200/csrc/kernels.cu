@@ -8,7 +8,7 @@
 //                            HBM write for k0-1 levels; the next block arrives by cp.async;
 //   * level8_kernel        : level 8 as two generated register phases per (panel, group chunk);
 //   * p1_inplace_kernel, p0_rows_kernel, phase_kernel : a level k >= 9 as in-place generated
-//                            stages 1..4 plus table-driven row-group phases for the later stages;
+//                            stages 1..5 plus interpreted row-group phases for the later stages;
 //   * level_kernel         : any level, table-driven column tiles (snfft_level, tests);
 //   * reorder_tiled_kernel / reorder_kernel : lexicographic <-> coset-major element order;
 //   * shard_exchange_kernel: the one exchange of the multi-GPU transform over peer memory;
@@ -1048,7 +1048,7 @@ phase_kernel(PhaseDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// stages 1..4 of a large level (k >= 9) as generated in-place register programs: one warp = one
+// stages 1..5 of a large level (k >= 9) as generated in-place register programs: one warp = one
 // (upper chain, 32-column tile), lanes = columns; plus the scaled row move of finished rows.
 // ---------------------------------------------------------------------------------------------
 template <bool INV>
@@ -1056,13 +1056,7 @@ __global__ void __launch_bounds__(256)
 p1_inplace_kernel(P1Dev P, double* __restrict__ xside, int64_t lgroups) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < P.nitems; item += (int64_t)gridDim.x * 8) {
-    // entries are sorted by sigma and item_off is increasing: binary search
-    int lo = 0, hi = P.nentries - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (P.entries[mid].item_off <= item) lo = mid; else hi = mid - 1;
-    }
-    const P1Entry e = P.entries[lo];
+    const P1Entry e = P.entries[P.item_entry[item]];  // entries are sorted by sigma: warps of a CTA share code
     const int c = (int)(item - e.item_off) * 32 + lane;
     if (c >= e.d) continue;
     for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y)
@@ -1075,12 +1069,7 @@ __global__ void __launch_bounds__(256)
 p0_rows_kernel(P1Dev P, double* __restrict__ xside, double* __restrict__ sside, int64_t lgroups) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < P.nrow_items; item += (int64_t)gridDim.x * 8) {
-    int lo = 0, hi = P.nrows - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (P.rows[mid].item_off <= item) lo = mid; else hi = mid - 1;
-    }
-    const P0Row r = P.rows[lo];
+    const P0Row r = P.rows[P.item_row[item]];
     const int c = (int)(item - r.item_off) * 32 + lane;
     if (c >= r.d) continue;
     for (int64_t lg = blockIdx.y; lg < lgroups; lg += gridDim.y) {
@@ -1702,6 +1691,72 @@ __global__ void wreath_permute_kernel(int N, int b, double* __restrict__ mat, do
   }
 }
 
+// Stage 2 of the wreath transform fused (small blocks): per coset pair (i, j) the b x b block
+//   sum_h F_i(t_i h t_j^-1) R[h]   (forward)      E[h] = <block, R[h]> scattered to F (adjoint)
+// with the gather index transposed to [h][pair] (coalesced), R[h] in shared memory, both planes
+// at once, and the block written straight into / read from the D x D matrices: one kernel instead
+// of gather + GEMM + permute per plane.  One thread = one coset pair.
+template <int BB, bool INV>
+__global__ void __launch_bounds__(256)
+wreath_stage2_kernel(int N, int b, int nH, const int64_t* __restrict__ idx_t, const double* __restrict__ R,
+                     double* __restrict__ Fre, double* __restrict__ Fim, double* __restrict__ Mre,
+                     double* __restrict__ Mim) {
+  extern __shared__ double Rs[];  // [nH][BB]
+  for (int e = threadIdx.x; e < nH * BB; e += 256) Rs[e] = R[e];
+  __syncthreads();
+  const int64_t pairs = (int64_t)N * N, D = (int64_t)N * b;
+  for (int64_t p = blockIdx.x * 256LL + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * 256) {
+    const int64_t i = p / N, j = p - i * N;
+    double ar[BB], ai[BB];
+    if (!INV) {
+#pragma unroll
+      for (int q = 0; q < BB; ++q) ar[q] = ai[q] = 0.0;
+      for (int h = 0; h < nH; ++h) {
+        const int64_t at = idx_t[(int64_t)h * pairs + p];
+        const double fr = Fre[at], fi = Fim[at];
+#pragma unroll
+        for (int q = 0; q < BB; ++q) {
+          const double r = Rs[h * BB + q];
+          ar[q] = fma(fr, r, ar[q]);
+          ai[q] = fma(fi, r, ai[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < BB; ++q) {
+        const int a = q / b, c = q - a * b;  // b * b == BB
+        Mre[(i * b + a) * D + j * b + c] = ar[q];
+        Mim[(i * b + a) * D + j * b + c] = ai[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < BB; ++q) {
+        const int a = q / b, c = q - a * b;
+        ar[q] = Mre[(i * b + a) * D + j * b + c];
+        ai[q] = Mim[(i * b + a) * D + j * b + c];
+      }
+      for (int h = 0; h < nH; ++h) {
+        double er = 0.0, ei = 0.0;
+#pragma unroll
+        for (int q = 0; q < BB; ++q) {
+          const double r = Rs[h * BB + q];
+          er = fma(ar[q], r, er);
+          ei = fma(ai[q], r, ei);
+        }
+        const int64_t at = idx_t[(int64_t)h * pairs + p];
+        Fre[at] = er;
+        Fim[at] = ei;
+      }
+    }
+  }
+}
+
+__global__ void transpose_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t rows, int64_t cols) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    out[c * rows + r] = in[e];
+  }
+}
+
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
@@ -1819,6 +1874,14 @@ cudaError_t prepare_kernels() {
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(dgemm_pipe_kernel, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<1, false>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<1, true>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<4, false>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<4, true>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<9, false>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<9, true>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<16, false>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<16, true>, 100)) != cudaSuccess) return e;
   // (kernels with static shared memory of their own: dynamic + static must stay <= 227 KB)
   if ((e = allow_big_smem(inverse_at_kernel, 200)) != cudaSuccess) return e;
   if ((e = allow_big_smem(c3_dft_kernel<false>, 200)) != cudaSuccess) return e;
@@ -2123,6 +2186,39 @@ cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, dou
   return cudaGetLastError();
 }
 
+cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  transpose_i64_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(in, out, rows, cols);
+  return cudaGetLastError();
+}
+
+bool wreath_stage2_fits(int N, int b, int nH) {
+  const int bb = b * b;
+  return (bb == 1 || bb == 4 || bb == 9 || bb == 16) && N >= 32 && (size_t)nH * bb * sizeof(double) <= 96 * 1024;
+}
+
+cudaError_t launch_wreath_stage2(int N, int b, int nH, const int64_t* idx_t, const double* R, double* Fre, double* Fim,
+                                 double* Mre, double* Mim, bool inverse, cudaStream_t stream) {
+  const int bb = b * b;
+  const size_t smem = (size_t)nH * bb * sizeof(double);
+  const unsigned grid = grid_for((int64_t)N * N);
+  LaunchScope scope(kKindDgemm, stream);
+#define SNFFT_S2(BBV)                                                                                             \
+  if (inverse)                                                                                                    \
+    wreath_stage2_kernel<BBV, true><<<grid, 256, smem, stream>>>(N, b, nH, idx_t, R, Fre, Fim, Mre, Mim);          \
+  else                                                                                                            \
+    wreath_stage2_kernel<BBV, false><<<grid, 256, smem, stream>>>(N, b, nH, idx_t, R, Fre, Fim, Mre, Mim)
+  switch (bb) {
+    case 1: SNFFT_S2(1); break;
+    case 4: SNFFT_S2(4); break;
+    case 9: SNFFT_S2(9); break;
+    case 16: SNFFT_S2(16); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef SNFFT_S2
+  return cudaGetLastError();
+}
+
 cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream) {
   LaunchScope scope(kKindOther, stream);
   transpose_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(in, out, rows, cols);
@@ -2138,7 +2234,7 @@ cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cud
 cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
                           int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
-  if (m < 1 || m > 9 || count > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (m < 1 || m > 8 || count > 0x7fffffffLL) return cudaErrorInvalidValue;
   int size = 1;
   for (int a = 0; a < m; ++a) size *= 3;
   const size_t smem = 2 * (size_t)size * sizeof(double);

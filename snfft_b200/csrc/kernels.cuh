@@ -35,8 +35,8 @@ cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const i
                          const int32_t* panel_pack, double* xside, double* sside, int64_t lgroups,
                          bool inverse, int num_sms, cudaStream_t stream);
 
-// Stages 1..4 of a large level as in-place generated programs plus the pass that moves the rows
-// finished after stage 4 to / from the spectrum-side buffer.
+// Stages 1..kP1Stages of a large level as in-place generated programs plus the pass that moves the
+// rows finished by then to / from the spectrum-side buffer.
 cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
                               int num_sms, cudaStream_t stream);
 
@@ -74,6 +74,11 @@ cudaError_t launch_wreath_index(int n, int N, int nH, const int8_t* T, const int
 cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, double scale, bool to_matrix,
                                   cudaStream_t stream);
 cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream);
+cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream);
+// stage 2 fused for small blocks (b*b in {1,4,9,16}, many cosets): gather + block sums + placement in one kernel
+bool wreath_stage2_fits(int N, int b, int nH);
+cudaError_t launch_wreath_stage2(int N, int b, int nH, const int64_t* idx_t, const double* R, double* Fre, double* Fim,
+                                 double* Mre, double* Mim, bool inverse, cudaStream_t stream);
 cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cudaStream_t stream);
 
 // dst[e][0..width) = src[idx[e]][0..width)

@@ -56,7 +56,7 @@ static_assert(sizeof(Block) == 32, "Block must be 32 bytes");
 // Inside one phase the rows of a panel fall into groups that are closed under the phase's blocks
 // (connected components of "block touches row"), so a CTA can load a bundle of groups for a tile of
 // columns into shared memory, run all their blocks stage by stage and store them back: one
-// coalesced pass over HBM per phase.  Phase 0 is always stages 1..4 (generated in-place programs).
+// coalesced pass over HBM per phase.  Phase 0 is always stages 1..kP1Stages (generated in-place programs).
 struct PhaseRow {
   uint32_t xoff;   // offset of the row in the X-side buffer (its in-place slot), start of the run
   uint32_t dest;   // offset of the finished row in the spectrum-side buffer
@@ -128,12 +128,16 @@ struct HostPlan {
 void build_host_plan(int n, HostPlan& plan);
 
 constexpr int kPhaseMinLevel = 9;   // levels >= 9 run as row-group phases
+// Stages 1..kP1Stages of a level >= 9 run as generated in-place register programs (one per shape of
+// W^5: the rows (i, t), i <= kP1Stages, t < d_sigma of one upper chain are closed under them: <= 36
+// rows); the windows of the phase kernel start at stage kP1Stages + 1.
+constexpr int kP1Stages = 5;
 constexpr int kPhaseMaxRows = 64;   // rows of a group (the phase kernel keeps the row table in two registers per lane)
 
-// Stage ranges of the phases of level k >= 9: [1..4] first, then the ranges given by their last
-// stages.  Default: 5..8 and 9..k-1 (groups of <= 48 rows, so that the tiles of the phase kernel can
-// be 256 columns wide); the environment variable SNFFT_WINDOWS overrides it for experiments, e.g.
-// "12:7,11/11:10" (per level the last stage of every phase after the first).
+// Stage ranges of the phases of level k >= 9: [1..kP1Stages] first, then the ranges given by their
+// last stages.  Default: windows of two stages, 6..7, 8..9, .. (groups of <= 8 rows: four column
+// chunks per warp in the phase kernel); the environment variable SNFFT_WINDOWS overrides it, e.g.
+// "12:9,11/11:10" (per level the last stage of every phase after the first).
 std::vector<std::pair<int, int>> phase_ranges(int k);
 
 // Dense rho_lambda((j j+1)) for shape `irrep` of level k (row-major d*d), from lattice chains.

@@ -292,7 +292,7 @@ class WreathPlan:
         self.mode = orientation_mode(self.oris, n) if m == 3 else None
         self.seg = np.repeat(np.arange(m), self.alpha)               # segment of position p
         self._c = None
-        if self.mode is not None and n <= 9:
+        if self.mode is not None and (n if self.mode == 'full' else n - 1) <= 8:
             # the standard C_3 layouts: the whole transform lives behind the C ABI (tables built in
             # C++ / on the device); this class is a thin caller
             a = np.array(self.alpha, dtype=np.int32)

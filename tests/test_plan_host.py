@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
     for name in declared:
         assert hasattr(N.lib, name)
-    assert N.lib.snfft_abi_version() == 1
+    assert N.lib.snfft_abi_version() == 2
 
 
 def test_plan_create_errors():
@@ -208,7 +208,7 @@ def test_reorder_tile_factorisation():
 
 
 def interpret_level_by_phases(plan, k, x, inverse=False):
-    """Level k >= 9 the way the device runs it: stages 1..4 in place on the X side (export_panel
+    """Level k >= 9 the way the device runs it: stages 1..5 in place on the X side (export_panel
     blocks; on the device these are the generated programs plus the finished-row move), then every
     row-group phase from the exported program blobs (what phase_kernel executes): per group load
     its rows, interpret the block stream, store rows in place or - when finished - to the
@@ -217,18 +217,19 @@ def interpret_level_by_phases(plan, k, x, inverse=False):
     kf = math.factorial(k)
     nphases = plan.export_phase(k, 1)['nphases']
     phases = [plan.export_phase(k, ph) for ph in range(1, nphases)]
+    p1_stages = phases[0]['stage_lo'] - 1          # stages 1..p1_stages: generated in-place programs
     xs = np.zeros(kf) if inverse else x.reshape(-1).copy()
     ss = x.reshape(-1).copy() if inverse else np.zeros(kf)
 
     def low_stages(inv):
         for pi, d in enumerate(dims):
             prog = plan.export_panel(k, pi)
-            low = [b for b in range(len(prog['m'])) if prog['stage'][b] <= 4]
+            low = [b for b in range(len(prog['m'])) if prog['stage'][b] <= p1_stages]
             last = {}
             for b in range(len(prog['m'])):
                 for a in range(prog['m'][b]):
                     last[prog['slots'][b, a]] = b
-            done_low = [s for s in range(k * d) if prog['stage'][last[s]] <= 4]
+            done_low = [s for s in range(k * d) if prog['stage'][last[s]] <= p1_stages]
             touched = sorted({int(v) for b in low for v in prog['slots'][b, :prog['m'][b]]})
             buf = {}
             for s in touched:
@@ -291,7 +292,7 @@ def interpret_level_by_phases(plan, k, x, inverse=False):
     return xs.reshape(k, kf // k)
 
 
-@pytest.mark.parametrize('windows', [None, '9:6,8'])
+@pytest.mark.parametrize('windows', [None, '9:7,8'])
 def test_phase_bundle_tables_reproduce_level_9(windows, monkeypatch):
     """The bundle tables of the row-group phases (device layout) against the plain block programs."""
     if windows:
