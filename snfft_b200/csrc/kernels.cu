@@ -1789,8 +1789,7 @@ __global__ void gather_kernel(const double* __restrict__ src, const int64_t* __r
 //   inverse (pull): spectra[b][idx[p]] = peer[r].cols[first_q + b][p - off[r]]
 // idx[off[r] .. off[r+1]) = positions of rank r's columns inside a packed S_m spectrum.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPullUnroll = 4;
-template <bool INV>
+template <bool INV, int UNROLL>
 __global__ void __launch_bounds__(256)
 shard_exchange_kernel(ShardPull X, double* __restrict__ local) {
   const int q = X.rank;
@@ -1799,12 +1798,12 @@ shard_exchange_kernel(ShardPull X, double* __restrict__ local) {
   for (int64_t b = blockIdx.y; b < nb; b += gridDim.y) {
     double* __restrict__ spec = local + b * X.mfact;
     const int64_t B = X.first[q] + b;
-    for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < X.mfact; p0 += stride * kPullUnroll) {
-      double v[kPullUnroll];
-      double* remote[kPullUnroll];
-      int at[kPullUnroll];
+    for (int p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < X.mfact; p0 += stride * UNROLL) {
+      double v[UNROLL];
+      double* remote[UNROLL];
+      int at[UNROLL];
 #pragma unroll
-      for (int u = 0; u < kPullUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         const int p = p0 + u * stride;
         at[u] = -1;
         if (p < X.mfact) {
@@ -1817,7 +1816,7 @@ shard_exchange_kernel(ShardPull X, double* __restrict__ local) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < kPullUnroll; ++u)
+      for (int u = 0; u < UNROLL; ++u)
         if (at[u] >= 0) {
           if (INV)
             spec[at[u]] = v[u];
@@ -2260,15 +2259,25 @@ cudaError_t launch_shard_pull(const ShardPull& X, double* local, bool inverse, c
   const int q = X.rank;
   const int64_t rows = X.first[q + 1] - X.first[q];
   if (rows <= 0 || X.mfact <= 0) return cudaSuccess;
-  int64_t gx = (X.mfact + 256 * kPullUnroll - 1) / (256 * kPullUnroll), gy = rows;
-  if (gx > 256) gx = 256;
+  // tuning knobs for the NVLink sweep (tools/exchange_sweep.sh): loads in flight per thread, CTAs per block row
+  static const int unroll = [] { const char* e = std::getenv("SNFFT_XCHG_UNROLL"); return e ? std::atoi(e) : 4; }();
+  // measured on 2 GPUs (S_12, 958 MB per rank per direction): 256 CTAs per block row with a grid-stride
+  // loop 456 GB/s, 1024: 532, 8192: 564, one CTA per 1024 positions (no loop): 579 GB/s
+  static const int gx_cap = [] { const char* e = std::getenv("SNFFT_XCHG_GX"); return e ? std::atoi(e) : 0x7fffffff; }();
+  const int un = unroll == 8 ? 8 : (unroll == 2 ? 2 : 4);
+  int64_t gx = (X.mfact + 256 * un - 1) / (256 * un), gy = rows;
+  if (gx > gx_cap) gx = gx_cap;
+  if (gx < 1) gx = 1;
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)gx, (unsigned)gy);
   LaunchScope scope(kKindExchange, stream);
-  if (inverse)
-    shard_exchange_kernel<true><<<grid, 256, 0, stream>>>(X, local);
-  else
-    shard_exchange_kernel<false><<<grid, 256, 0, stream>>>(X, local);
+#define SNFFT_XCHG(U)                                                             \
+  if (inverse)                                                                    \
+    shard_exchange_kernel<true, U><<<grid, 256, 0, stream>>>(X, local);           \
+  else                                                                            \
+    shard_exchange_kernel<false, U><<<grid, 256, 0, stream>>>(X, local)
+  if (un == 8) { SNFFT_XCHG(8); } else if (un == 2) { SNFFT_XCHG(2); } else { SNFFT_XCHG(4); }
+#undef SNFFT_XCHG
   return cudaGetLastError();
 }
 
