@@ -53,7 +53,29 @@ def test_host_only_plan_refuses_device_work():
     assert N.lib.snfft_shard_exchange(shard, peers, N.ptr(buf), 0, None) == 2
     assert N.lib.snfft_shard_exchange(shard, None, N.ptr(buf), 0, None) == 1
     assert N.lib.snfft_shard_exchange(None, peers, N.ptr(buf), 0, None) == 1
+    # the whole-schedule entry points, the sampled inverse, the seminormal form and the wreath plan
+    # refuse the same way: no device, no result (and no CPU path behind them)
+    ws = N.ShardWorkspace()
+    ws.local_a = ws.local_b = ws.shard_a = ws.shard_b = ws.status = N.ptr(buf).value
+    assert N.lib.snfft_forward_sharded(shard, N.ptr(buf), N.ptr(buf.copy()), C.byref(ws), None) == 2
+    assert N.lib.snfft_inverse_sharded(shard, N.ptr(buf), N.ptr(buf.copy()), C.byref(ws), None) == 2
+    assert N.lib.snfft_forward_sharded(shard, None, N.ptr(buf), C.byref(ws), None) == 1
+    sizes = (C.c_int64 * 4)()
+    assert N.lib.snfft_shard_ws_sizes(shard, sizes) == 0
+    # 4 blocks of S_3, 2 per rank; rank 1 owns the larger column share (4 of the 6 entries of a spectrum)
+    assert sizes[0] == 4 * 4 and sizes[1] == 2 * 6 and sizes[2] == 0 and sizes[3] == 32
     N.lib.snfft_shard_destroy(shard)
+    perms = np.array([[1, 2, 3, 4]], dtype=np.int32)
+    assert N.lib.snfft_inverse_at(plan._h, N.ptr(buf), N.ptr(perms), 1, N.ptr(buf.copy()), None) == 2
+    assert N.lib.snfft_ysemi(plan._h, 1, N.ptr(perms), 1, N.ptr(buf.copy()), None) == 2
+    alpha = np.array([1, 2, 1], dtype=np.int32)
+    parts = np.zeros((3, 4), dtype=np.int32)
+    parts[0, 0], parts[1, 0], parts[2, 0] = 1, 2, 1
+    assert N.lib.snfft_wreath_create(4, N.ptr(alpha), N.ptr(parts), 0, -1, C.byref(C.c_void_p())) == 2
+    assert b'no CPU fallback' in N.lib.snfft_last_error()
+    assert N.lib.snfft_wreath_create(4, N.ptr(np.array([1, 1, 1], dtype=np.int32)), N.ptr(parts), 0, -1,
+                                     C.byref(C.c_void_p())) == 1
+    assert N.lib.snfft_c3_dft(9, N.ptr(buf), None, N.ptr(perms), 1, 1, N.ptr(buf), N.ptr(buf), 0, None) == 1
 
 
 @pytest.mark.parametrize('n', range(1, 11))
