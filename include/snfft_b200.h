@@ -255,7 +255,8 @@ int snfft_wreath_dims(const snfft_wreath* plan, int64_t* dims);
 int snfft_wreath_forward(snfft_wreath* plan, const double* f_dev, double* out_re_dev, double* out_im_dev,
                          void* stream);
 /* D tr(rho(g)^H f_hat) / |G| at every group element (cube_ift.py:56-67, fft.py:158-172 divided by
- * the group order): out planes double[n!][orientations]. */
+ * the group order): out planes double[n!][orientations]; with out_im_dev == NULL the result is
+ * written to out_re_dev as interleaved complex128 [n!][orientations] (16-byte aligned). */
 int snfft_wreath_inverse(snfft_wreath* plan, const double* fhat_re_dev, const double* fhat_im_dev,
                          double* out_re_dev, double* out_im_dev, void* stream);
 
@@ -270,7 +271,11 @@ int snfft_dgemm(const double* a_dev, const double* b_dev, double* c_dev, int64_t
  * significant) is transformed with m radix-3 passes in shared memory and only the nfreq frequencies
  * listed in freq_dev (same indexing) are written: out[count][nfreq] = sum_o in[o] omega^{+k.o}.
  * inverse != 0 is the adjoint: in [count][nfreq] complex is scattered onto the frequency grid and
- * out [count][3^m] = sum_k in[k] omega^{-k.o} (no normalisation).  m <= 8. */
+ * out [count][3^m] = sum_k in[k] omega^{-k.o} (no normalisation).  Complex data are two planes, or
+ * interleaved complex128 (16-byte aligned) where the second pointer is NULL: out_im_dev == NULL
+ * (either direction) writes complex128 to out_re_dev, in_im_dev == NULL with inverse != 0 reads
+ * complex128 from in_re_dev (the forward input is real: in_im_dev is ignored, and two rows share
+ * one complex transform).  m <= 8. */
 int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
                  int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream);
 /* dst[e][0..width) = src[idx[e]][0..width) for e < count: regroups S_n by cosets of a Young

@@ -1676,10 +1676,11 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
       CUDA_OK(launch_transpose_i64(w->idx, w->idx_t, w->N * w->N, w->nH, nullptr));
     }
     // ---- workspace ----
-    w->Fre = w->alloc<double>((size_t)w->nfact * w->N);
-    w->Fim = w->alloc<double>((size_t)w->nfact * w->N);
+    // F_i(sigma): two planes, or - for the fused stage 2 - the same memory as interleaved complex128
+    w->Fre = w->alloc<double>(2 * (size_t)w->nfact * w->N);
+    w->Fim = w->Fre + (size_t)w->nfact * w->N;
     w->G = w->alloc<double>((size_t)w->nfact * w->N);
-    w->P = w->alloc<double>((size_t)w->N * w->N * bb);
+    w->P = w->alloc<double>(2 * (size_t)w->N * w->N * bb);  // one plane of blocks (GEMM path) or complex blocks (fused adjoint)
     if (w->sn_plan) {
       w->sn_spec = w->alloc<double>((size_t)w->nfact);
       w->sn_work = w->alloc<double>((size_t)w->nfact);
@@ -1726,7 +1727,9 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
     std::lock_guard<std::mutex> lock(w->mu);
     const int64_t bb = w->block * w->block, pairs = w->N * w->N;
     // stage 1: character sums over the orientations, F_i(sigma) (one pass over f)
-    CUDA_OK(launch_c3_dft(w->m, f_dev, nullptr, w->freq, (int)w->N, w->nfact, w->Fre, w->Fim, false, stream));
+    const bool fused = w->idx_t && !w->sn_plan;  // F interleaved (see snfft_wreath_create)
+    CUDA_OK(launch_c3_dft(w->m, f_dev, nullptr, w->freq, (int)w->N, w->nfact, w->Fre, fused ? nullptr : w->Fim, false,
+                          1.0, stream));
     // stage 2: per coset pair the sum over the Young subgroup.  One coset (S_alpha = S_n): the S_n
     // transform of F itself - the same level recursion as snfft_forward, from lexicographic order -
     // and the block of the irrep `parts` out of the packed spectrum.  Small blocks: one fused kernel;
@@ -1739,9 +1742,9 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
       }
       return;
     }
-    if (w->idx_t) {
-      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->idx_t, w->R, w->Fre, w->Fim, out_re_dev,
-                                   out_im_dev, false, stream));
+    if (fused) {
+      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->nfact, w->idx_t, w->inv_idx, w->R, w->Fre,
+                                   out_re_dev, out_im_dev, w->P, false, stream));
       return;
     }
     for (int plane = 0; plane < 2; ++plane) {
@@ -1755,7 +1758,8 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
 int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const double* fhat_im_dev, double* out_re_dev,
                          double* out_im_dev, void* stream_) {
   return guarded([&] {
-    if (!w || !fhat_re_dev || !fhat_im_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null argument");
+    if (!w || !fhat_re_dev || !fhat_im_dev || !out_re_dev) throw InvalidArg("null argument");
+    if (!out_im_dev) require_aligned16(out_re_dev, "out_re_dev (interleaved complex128 output)");
     DeviceGuard guard(w->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lock(w->mu);
@@ -1766,25 +1770,27 @@ int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const doubl
       CUDA_OK(launch_dgemm(w->P, w->RT, w->G, (int)pairs, (int)w->nH, (int)bb, stream));  // [pairs][nH]
       CUDA_OK(launch_gather(w->G, w->inv_idx, plane ? w->Fim : w->Fre, w->nfact * w->N, 1, stream));
     }
-    if (w->idx_t)
-      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->idx_t, w->R, w->Fre, w->Fim,
-                                   const_cast<double*>(fhat_re_dev), const_cast<double*>(fhat_im_dev), true, stream));
-    CUDA_OK(launch_c3_dft(w->m, w->Fre, w->Fim, w->freq, (int)w->N, w->nfact, out_re_dev, out_im_dev, true, stream));
-    // d tr(rho(g)^H f_hat) / |G| (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140)
-    CUDA_OK(launch_scale2(out_re_dev, out_im_dev, w->nfact * w->n_ori, (double)w->D / ((double)w->nfact * (double)w->n_ori), stream));
+    if (w->idx_t)  // fused: F interleaved, written coalesced (one thread per element of F)
+      CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->nfact, w->idx_t, w->inv_idx, w->R, w->Fre,
+                                   const_cast<double*>(fhat_re_dev), const_cast<double*>(fhat_im_dev), w->P, true, stream));
+    // d tr(rho(g)^H f_hat) / |G| (cube_ift.py:56-67 divided by the group order, test_inv_fft.py:140):
+    // the factor rides on the N values the adjoint DFT scatters onto its grid
+    CUDA_OK(launch_c3_dft(w->m, w->Fre, w->idx_t ? nullptr : w->Fim, w->freq, (int)w->N, w->nfact, out_re_dev, out_im_dev, true,
+                          (double)w->D / ((double)w->nfact * (double)w->n_ori), stream));
   });
 }
 
 int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
                  int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream) {
   return guarded([&] {
-    if (!in_re_dev || !freq_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null device buffer");
-    if (inverse && !in_im_dev) throw InvalidArg("the adjoint transform needs the imaginary plane");
+    if (!in_re_dev || !freq_dev || !out_re_dev) throw InvalidArg("null device buffer");
+    if (!out_im_dev) require_aligned16(out_re_dev, "out_re_dev (interleaved complex128 output)");
+    if (inverse && !in_im_dev) require_aligned16(in_re_dev, "in_re_dev (interleaved complex128 input)");
     if (m < 1 || m > 8) throw InvalidArg("m must be in 1..8 (the 3^m grid lives in shared memory)");
     if (nfreq < 1 || count < 0) throw InvalidArg("bad shape");
     ensure_kernels_prepared();
     CUDA_OK(launch_c3_dft(m, in_re_dev, in_im_dev, freq_dev, nfreq, count, out_re_dev, out_im_dev, inverse != 0,
-                          (cudaStream_t)stream));
+                          1.0, (cudaStream_t)stream));
   });
 }
 

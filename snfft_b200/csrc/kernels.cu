@@ -1325,9 +1325,12 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
 // the N values are scattered onto the frequency grid and the conjugate DFT gives all 3^m values.
 // ---------------------------------------------------------------------------------------------
 // D consecutive base-3 digits (strides s, 3s, .. of the grid) transformed in registers: a 3^D-point
-// DFT per thread, D radix-3 stages on compile-time indices, one shared-memory round trip
-template <int D, bool INV>
-__device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __restrict__ im, int base, int s) {
+// DFT per thread, D radix-3 stages on compile-time indices, one shared-memory round trip.
+// OUT = 0: back to shared memory; 1: straight to the global output planes (the last pass of the
+// adjoint); 2: the same as interleaved complex128 (one 16-byte store per point).
+template <int D, bool INV, int OUT>
+__device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __restrict__ im, int base, int s,
+                                          double* __restrict__ gre, double* __restrict__ gim) {
   constexpr int P = D == 1 ? 3 : (D == 2 ? 9 : 27);
   const double h = INV ? -0.8660254037844386467637231707529 : 0.8660254037844386467637231707529;  // +-sqrt(3)/2
   double xr[P], xi[P];
@@ -1358,50 +1361,85 @@ __device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __res
   }
 #pragma unroll
   for (int j = 0; j < P; ++j) {
-    re[base + j * s] = xr[j];
-    im[base + j * s] = xi[j];
+    if (OUT == 2) {
+      reinterpret_cast<double2*>(gre)[base + j * s] = make_double2(xr[j], xi[j]);
+    } else if (OUT == 1) {
+      gre[base + j * s] = xr[j];
+      gim[base + j * s] = xi[j];
+    } else {
+      re[base + j * s] = xr[j];
+      im[base + j * s] = xi[j];
+    }
   }
 }
 
 constexpr int kDftThreads = 128;
 
-template <bool INV>
+// Forward: the input rows are REAL, so one complex transform serves TWO rows: z = f(s1,.) + i f(s2,.),
+// Z = DFT(z), and F_1(k) = (Z(k) + conj Z(-k)) / 2, F_2(k) = (Z(k) - conj Z(-k)) / 2i.  One CTA =
+// one pair of rows; half the arithmetic and half the shared-memory traffic per row.  The adjoint
+// (complex in, complex out) has no such symmetry: one CTA = one row, the factor `scale` rides on
+// the nfreq scattered values and the last pass stores to global memory from registers (lanes run
+// along the low digits: coalesced).  INTERLEAVED: the output is complex128 in out_re instead of
+// two planes; in_im == nullptr: the adjoint's input is complex128 in in_re.
+template <bool INV, bool INTERLEAVED>
 __global__ void __launch_bounds__(kDftThreads)
-c3_dft_kernel(int m, int size, const double* __restrict__ in_re, const double* __restrict__ in_im,
+c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, const double* __restrict__ in_im,
               const int32_t* __restrict__ freq, int nfreq, double* __restrict__ out_re,
-              double* __restrict__ out_im) {
+              double* __restrict__ out_im, double scale) {
   extern __shared__ double grid[];
   double* re = grid;
   double* im = grid + size;
-  const int64_t sig = blockIdx.x;
+  const int64_t sig = INV ? (int64_t)blockIdx.x : 2 * (int64_t)blockIdx.x;
+  const bool second = !INV && sig + 1 < count;
   if (!INV) {
     for (int e = threadIdx.x; e < size; e += kDftThreads) {
       re[e] = in_re[sig * size + e];
-      im[e] = 0.0;
+      im[e] = second ? in_re[(sig + 1) * size + e] : 0.0;
     }
   } else {
     for (int e = threadIdx.x; e < size; e += kDftThreads) re[e] = im[e] = 0.0;
     __syncthreads();
     for (int i = threadIdx.x; i < nfreq; i += kDftThreads) {
-      re[freq[i]] = in_re[sig * nfreq + i];
-      im[freq[i]] = in_im[sig * nfreq + i];
+      double vr, vi;
+      if (in_im) {
+        vr = in_re[sig * nfreq + i];
+        vi = in_im[sig * nfreq + i];
+      } else {
+        const double2 v = reinterpret_cast<const double2*>(in_re)[sig * nfreq + i];
+        vr = v.x;
+        vi = v.y;
+      }
+      re[freq[i]] = scale * vr;
+      im[freq[i]] = scale * vi;
     }
   }
   __syncthreads();
   // forward: omega^{+k o}; adjoint: omega^{-k o}.  Two digits per pass (9 points per thread in
   // registers: 243 independent sub-transforms per pass for the 2x2 cube, ~80 registers), then the
-  // odd digit: 4 barriers instead of 7
+  // odd digit: 4 barriers instead of 7.  (Three digits per pass - 27 points, 168..190 registers,
+  // 3 passes - measured slower: 0.63 vs 0.56 ms for the cube, too few warps per SM.)
+  double* gre = INTERLEAVED ? out_re + 2 * sig * size : out_re + sig * size;
+  double* gim = INTERLEAVED ? nullptr : out_im + sig * size;
   int done = 0, stride = 1;
   while (done < m) {
     const int dg = m - done >= 2 ? 2 : 1;
     const int pts = dg == 2 ? 9 : 3;
+    const bool to_global = INV && done + dg == m;
     for (int t = threadIdx.x; t < size / pts; t += kDftThreads) {
       const int hi = t / stride, lo = t - hi * stride;
       const int base = hi * pts * stride + lo;
-      if (dg == 2)
-        c3_digits<2, INV>(re, im, base, stride);
-      else
-        c3_digits<1, INV>(re, im, base, stride);
+      if (dg == 2) {
+        if (to_global)
+          c3_digits<2, INV, INTERLEAVED ? 2 : 1>(re, im, base, stride, gre, gim);
+        else
+          c3_digits<2, INV, 0>(re, im, base, stride, nullptr, nullptr);
+      } else {
+        if (to_global)
+          c3_digits<1, INV, INTERLEAVED ? 2 : 1>(re, im, base, stride, gre, gim);
+        else
+          c3_digits<1, INV, 0>(re, im, base, stride, nullptr, nullptr);
+      }
     }
     __syncthreads();
     done += dg;
@@ -1409,13 +1447,26 @@ c3_dft_kernel(int m, int size, const double* __restrict__ in_re, const double* _
   }
   if (!INV) {
     for (int i = threadIdx.x; i < nfreq; i += kDftThreads) {
-      out_re[sig * nfreq + i] = re[freq[i]];
-      out_im[sig * nfreq + i] = im[freq[i]];
-    }
-  } else {
-    for (int e = threadIdx.x; e < size; e += kDftThreads) {
-      out_re[sig * size + e] = re[e];
-      out_im[sig * size + e] = im[e];
+      const int k = freq[i];
+      int kn = 0;  // the index of -k: every base-3 digit negated
+      for (int a = 0, r = k, p = 1; a < m; ++a, p *= 3) {
+        const int d = r % 3;
+        r /= 3;
+        kn += (d == 0 ? 0 : 3 - d) * p;
+      }
+      const double zr = re[k], zi = im[k], wr = re[kn], wi = im[kn];
+      if (INTERLEAVED) {
+        double2* o = reinterpret_cast<double2*>(out_re);
+        o[sig * nfreq + i] = make_double2(0.5 * (zr + wr), 0.5 * (zi - wi));
+        if (second) o[(sig + 1) * nfreq + i] = make_double2(0.5 * (zi + wi), 0.5 * (wr - zr));
+      } else {
+        out_re[sig * nfreq + i] = 0.5 * (zr + wr);
+        out_im[sig * nfreq + i] = 0.5 * (zi - wi);
+        if (second) {
+          out_re[(sig + 1) * nfreq + i] = 0.5 * (zi + wi);
+          out_im[(sig + 1) * nfreq + i] = 0.5 * (wr - zr);
+        }
+      }
     }
   }
 }
@@ -1692,15 +1743,15 @@ __global__ void wreath_permute_kernel(int N, int b, double* __restrict__ mat, do
 }
 
 // Stage 2 of the wreath transform fused (small blocks): per coset pair (i, j) the b x b block
-//   sum_h F_i(t_i h t_j^-1) R[h]   (forward)      E[h] = <block, R[h]> scattered to F (adjoint)
-// with the gather index transposed to [h][pair] (coalesced), R[h] in shared memory, both planes
-// at once, and the block written straight into / read from the D x D matrices: one kernel instead
-// of gather + GEMM + permute per plane.  One thread = one coset pair.
-template <int BB, bool INV>
+//   sum_h F_i(t_i h t_j^-1) R[h]
+// with the gather index transposed to [h][pair] (coalesced), R[h] in shared memory, F as
+// interleaved complex128 (one 16-byte gather per term instead of two 8-byte ones in different
+// sectors), and the block written straight into the D x D matrices: one kernel instead of gather +
+// GEMM + permute per plane.  One thread = one coset pair.
+template <int BB>
 __global__ void __launch_bounds__(256)
 wreath_stage2_kernel(int N, int b, int nH, const int64_t* __restrict__ idx_t, const double* __restrict__ R,
-                     double* __restrict__ Fre, double* __restrict__ Fim, double* __restrict__ Mre,
-                     double* __restrict__ Mim) {
+                     const double2* __restrict__ F, double* __restrict__ Mre, double* __restrict__ Mim) {
   extern __shared__ double Rs[];  // [nH][BB]
   for (int e = threadIdx.x; e < nH * BB; e += 256) Rs[e] = R[e];
   __syncthreads();
@@ -1708,45 +1759,65 @@ wreath_stage2_kernel(int N, int b, int nH, const int64_t* __restrict__ idx_t, co
   for (int64_t p = blockIdx.x * 256LL + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * 256) {
     const int64_t i = p / N, j = p - i * N;
     double ar[BB], ai[BB];
-    if (!INV) {
 #pragma unroll
-      for (int q = 0; q < BB; ++q) ar[q] = ai[q] = 0.0;
-      for (int h = 0; h < nH; ++h) {
-        const int64_t at = idx_t[(int64_t)h * pairs + p];
-        const double fr = Fre[at], fi = Fim[at];
-#pragma unroll
-        for (int q = 0; q < BB; ++q) {
-          const double r = Rs[h * BB + q];
-          ar[q] = fma(fr, r, ar[q]);
-          ai[q] = fma(fi, r, ai[q]);
-        }
-      }
+    for (int q = 0; q < BB; ++q) ar[q] = ai[q] = 0.0;
+    for (int h = 0; h < nH; ++h) {
+      const double2 fv = F[idx_t[(int64_t)h * pairs + p]];
 #pragma unroll
       for (int q = 0; q < BB; ++q) {
-        const int a = q / b, c = q - a * b;  // b * b == BB
-        Mre[(i * b + a) * D + j * b + c] = ar[q];
-        Mim[(i * b + a) * D + j * b + c] = ai[q];
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < BB; ++q) {
-        const int a = q / b, c = q - a * b;
-        ar[q] = Mre[(i * b + a) * D + j * b + c];
-        ai[q] = Mim[(i * b + a) * D + j * b + c];
-      }
-      for (int h = 0; h < nH; ++h) {
-        double er = 0.0, ei = 0.0;
-#pragma unroll
-        for (int q = 0; q < BB; ++q) {
-          const double r = Rs[h * BB + q];
-          er = fma(ar[q], r, er);
-          ei = fma(ai[q], r, ei);
-        }
-        const int64_t at = idx_t[(int64_t)h * pairs + p];
-        Fre[at] = er;
-        Fim[at] = ei;
+        const double r = Rs[h * BB + q];
+        ar[q] = fma(fv.x, r, ar[q]);
+        ai[q] = fma(fv.y, r, ai[q]);
       }
     }
+#pragma unroll
+    for (int q = 0; q < BB; ++q) {
+      const int a = q / b, c = q - a * b;  // b * b == BB
+      Mre[(i * b + a) * D + j * b + c] = ar[q];
+      Mim[(i * b + a) * D + j * b + c] = ai[q];
+    }
+  }
+}
+
+// The adjoint of stage 2, F-major: every (sigma, i) belongs to exactly one (coset pair, h)
+// (sigma = t_i h t_j^-1: inv_idx), so one thread = one element of F:
+//   F_i(sigma) = <block(i, j), R[h]>
+// reads the blocks (L2-resident gathers) and WRITES F coalesced - the pair-major form scattered
+// 8-byte stores over F (ncu: 0.8 GB read + 1.0 GB written for 0.36 GB of results).  The blocks are
+// first regrouped from the two D x D planes into [pair][BB] complex128 (wreath_blocks_kernel): one
+// contiguous 16 BB-byte gather per element instead of 2 BB 8-byte ones (L2 traffic 6.4 -> 1.5 GB).
+__global__ void wreath_blocks_kernel(int N, int b, const double* __restrict__ Mre, const double* __restrict__ Mim,
+                                     double2* __restrict__ blocks) {
+  const int64_t D = (int64_t)N * b, total = D * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / D, col = e - row * D;
+    const int64_t i = row / b, a = row - i * b, j = col / b, c = col - j * b;
+    blocks[(i * N + j) * b * b + a * b + c] = make_double2(Mre[e], Mim[e]);
+  }
+}
+
+template <int BB>
+__global__ void __launch_bounds__(256)
+wreath_stage2_adjoint_kernel(int nH, int64_t total, const int64_t* __restrict__ inv_idx,
+                             const double* __restrict__ R, double2* __restrict__ F,
+                             const double2* __restrict__ blocks) {
+  extern __shared__ double Rs[];  // [nH][BB]
+  for (int e = threadIdx.x; e < nH * BB; e += 256) Rs[e] = R[e];
+  __syncthreads();
+  for (int64_t at = blockIdx.x * 256LL + threadIdx.x; at < total; at += (int64_t)gridDim.x * 256) {
+    const uint64_t e = (uint64_t)inv_idx[at];  // (i N + j) nH + h
+    const uint64_t pair = e / (uint64_t)nH;
+    const int h = (int)(e - pair * (uint64_t)nH);
+    const double2* __restrict__ blk = blocks + pair * BB;
+    double er = 0.0, ei = 0.0;
+#pragma unroll
+    for (int q = 0; q < BB; ++q) {
+      const double2 v = blk[q];
+      const double r = Rs[h * BB + q];
+      er = fma(v.x, r, er);
+      ei = fma(v.y, r, ei);
+    }
+    F[at] = make_double2(er, ei);
   }
 }
 
@@ -1761,13 +1832,6 @@ __global__ void transpose_kernel(const double* __restrict__ in, double* __restri
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
     out[c * rows + r] = in[e];
-  }
-}
-
-__global__ void scale2_kernel(double* __restrict__ a, double* __restrict__ b, int64_t count, double scale) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
-    a[e] *= scale;
-    b[e] *= scale;
   }
 }
 
@@ -1873,18 +1937,20 @@ cudaError_t prepare_kernels() {
   if ((e = allow_big_smem(level_kernel<false>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(level_kernel<true>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(dgemm_pipe_kernel, 200)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<1, false>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<1, true>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<4, false>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<4, true>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<9, false>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<9, true>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<16, false>, 100)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(wreath_stage2_kernel<16, true>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<1>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_adjoint_kernel<1>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<4>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_adjoint_kernel<4>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<9>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_adjoint_kernel<9>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_kernel<16>, 100)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(wreath_stage2_adjoint_kernel<16>, 100)) != cudaSuccess) return e;
   // (kernels with static shared memory of their own: dynamic + static must stay <= 227 KB)
   if ((e = allow_big_smem(inverse_at_kernel, 200)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(c3_dft_kernel<false>, 200)) != cudaSuccess) return e;
-  if ((e = allow_big_smem(c3_dft_kernel<true>, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<false, false>, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<false, true>, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<true, false>, 200)) != cudaSuccess) return e;
+  if ((e = allow_big_smem(c3_dft_kernel<true, true>, 200)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 1>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<true, 1>)) != cudaSuccess) return e;
   if ((e = allow_big_smem(phase_kernel<false, 2>)) != cudaSuccess) return e;
@@ -2196,17 +2262,25 @@ bool wreath_stage2_fits(int N, int b, int nH) {
   return (bb == 1 || bb == 4 || bb == 9 || bb == 16) && N >= 32 && (size_t)nH * bb * sizeof(double) <= 96 * 1024;
 }
 
-cudaError_t launch_wreath_stage2(int N, int b, int nH, const int64_t* idx_t, const double* R, double* Fre, double* Fim,
-                                 double* Mre, double* Mim, bool inverse, cudaStream_t stream) {
+cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int64_t* idx_t, const int64_t* inv_idx,
+                                 const double* R, double* F, double* Mre, double* Mim, double* blocks, bool inverse,
+                                 cudaStream_t stream) {
   const int bb = b * b;
   const size_t smem = (size_t)nH * bb * sizeof(double);
-  const unsigned grid = grid_for((int64_t)N * N);
+  const int64_t total = nfact * N;  // elements of F = (coset pairs) x |S_alpha|
+  const unsigned grid = inverse ? grid_for(total) : grid_for((int64_t)N * N);
+  double2* F2 = reinterpret_cast<double2*>(F);
+  double2* B2 = reinterpret_cast<double2*>(blocks);
+  if (inverse) {
+    LaunchScope scope(kKindOther, stream);
+    wreath_blocks_kernel<<<grid_for((int64_t)N * b * N * b), 256, 0, stream>>>(N, b, Mre, Mim, B2);
+  }
   LaunchScope scope(kKindDgemm, stream);
-#define SNFFT_S2(BBV)                                                                                             \
-  if (inverse)                                                                                                    \
-    wreath_stage2_kernel<BBV, true><<<grid, 256, smem, stream>>>(N, b, nH, idx_t, R, Fre, Fim, Mre, Mim);          \
-  else                                                                                                            \
-    wreath_stage2_kernel<BBV, false><<<grid, 256, smem, stream>>>(N, b, nH, idx_t, R, Fre, Fim, Mre, Mim)
+#define SNFFT_S2(BBV)                                                                                          \
+  if (inverse)                                                                                                 \
+    wreath_stage2_adjoint_kernel<BBV><<<grid, 256, smem, stream>>>(nH, total, inv_idx, R, F2, B2);              \
+  else                                                                                                         \
+    wreath_stage2_kernel<BBV><<<grid, 256, smem, stream>>>(N, b, nH, idx_t, R, F2, Mre, Mim)
   switch (bb) {
     case 1: SNFFT_S2(1); break;
     case 4: SNFFT_S2(4); break;
@@ -2224,24 +2298,27 @@ cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_
   return cudaGetLastError();
 }
 
-cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cudaStream_t stream) {
-  LaunchScope scope(kKindOther, stream);
-  scale2_kernel<<<grid_for(count), 256, 0, stream>>>(a, b, count, scale);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
-                          int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream) {
+                          int64_t count, double* out_re, double* out_im, bool inverse, double scale,
+                          cudaStream_t stream) {
   if (count <= 0) return cudaSuccess;
   if (m < 1 || m > 8 || count > 0x7fffffffLL) return cudaErrorInvalidValue;
   int size = 1;
   for (int a = 0; a < m; ++a) size *= 3;
   const size_t smem = 2 * (size_t)size * sizeof(double);
   LaunchScope scope(kKindOther, stream);
-  if (inverse)
-    c3_dft_kernel<true><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+  if (!inverse && out_im)
+    c3_dft_kernel<false, false><<<(unsigned)((count + 1) / 2), kDftThreads, smem, stream>>>(
+        m, size, count, in_re, in_im, freq, nfreq, out_re, out_im, scale);
+  else if (!inverse)
+    c3_dft_kernel<false, true><<<(unsigned)((count + 1) / 2), kDftThreads, smem, stream>>>(
+        m, size, count, in_re, in_im, freq, nfreq, out_re, out_im, scale);
+  else if (out_im)
+    c3_dft_kernel<true, false><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, count, in_re, in_im, freq,
+                                                                               nfreq, out_re, out_im, scale);
   else
-    c3_dft_kernel<false><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, in_re, in_im, freq, nfreq, out_re, out_im);
+    c3_dft_kernel<true, true><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, count, in_re, in_im, freq,
+                                                                              nfreq, out_re, out_im, scale);
   return cudaGetLastError();
 }
 

@@ -64,9 +64,11 @@ cudaError_t launch_dgemm(const double* A, const double* B, double* C, int M, int
                          cudaStream_t stream);
 
 // DFT over C_3^m of `count` rows: forward real [count][3^m] -> complex at the nfreq listed frequency
-// indices; inverse (adjoint): complex [count][nfreq] -> complex [count][3^m].
+// indices; inverse (adjoint): complex [count][nfreq] -> scale * complex [count][3^m].  out_im == nullptr:
+// the output is interleaved complex128 in out_re; inverse with in_im == nullptr: so is the input.
 cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const int32_t* freq, int nfreq,
-                          int64_t count, double* out_re, double* out_im, bool inverse, cudaStream_t stream);
+                          int64_t count, double* out_re, double* out_im, bool inverse, double scale,
+                          cudaStream_t stream);
 
 // tables and layout helpers of the wreath plan (capi.cu: snfft_wreath_*)
 cudaError_t launch_wreath_index(int n, int N, int nH, const int8_t* T, const int8_t* Tinv, const int8_t* H,
@@ -77,9 +79,10 @@ cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_
 cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream);
 // stage 2 fused for small blocks (b*b in {1,4,9,16}, many cosets): gather + block sums + placement in one kernel
 bool wreath_stage2_fits(int N, int b, int nH);
-cudaError_t launch_wreath_stage2(int N, int b, int nH, const int64_t* idx_t, const double* R, double* Fre, double* Fim,
-                                 double* Mre, double* Mim, bool inverse, cudaStream_t stream);
-cudaError_t launch_scale2(double* a, double* b, int64_t count, double scale, cudaStream_t stream);
+// F: interleaved complex128 [n!][N]; forward reads it through idx_t ([h][pair]), the adjoint writes it through inv_idx
+cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int64_t* idx_t, const int64_t* inv_idx,
+                                 const double* R, double* F, double* Mre, double* Mim, double* blocks, bool inverse,
+                                 cudaStream_t stream);  // blocks: 2 N^2 b^2 doubles of scratch (adjoint)
 
 // dst[e][0..width) = src[idx[e]][0..width)
 cudaError_t launch_gather(const double* src, const int64_t* idx, double* dst, int64_t count, int width,

@@ -439,13 +439,12 @@ class WreathPlan:
         import torch
         if self._c is not None:
             fre, fim = fhat.real.contiguous(), fhat.imag.contiguous()
-            shape = (math.factorial(self.n), len(self.oris))
-            re = torch.empty(shape, dtype=torch.float64, device=fhat.device)
-            im = torch.empty(shape, dtype=torch.float64, device=fhat.device)
+            # interleaved complex128 straight from the kernel (out_im = NULL): no plane merge pass
+            out = torch.empty((math.factorial(self.n), len(self.oris)), dtype=torch.complex128, device=fhat.device)
             with torch.cuda.device(self.device):
-                N.check(N.lib.snfft_wreath_inverse(self._c, N.ptr(fre), N.ptr(fim), N.ptr(re), N.ptr(im),
+                N.check(N.lib.snfft_wreath_inverse(self._c, N.ptr(fre), N.ptr(fim), N.ptr(out), None,
                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-            return torch.complex(re, im)
+            return out
         B = fhat.reshape(self.N, self.block, self.N, self.block).permute(0, 2, 1, 3).reshape(
             self.N * self.N, self.block * self.block)
         with torch.cuda.device(self.device):

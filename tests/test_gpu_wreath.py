@@ -261,3 +261,39 @@ def test_c_abi_wreath_plan_without_the_python_classes():
     bad = np.array([1, 1, 1], dtype=np.int32)
     assert N.lib.snfft_wreath_create(5, N.ptr(bad), N.ptr(np.zeros((3, 5), dtype=np.int32)), 0, 0,
                                      C.byref(C.c_void_p())) == 1
+
+
+@pytest.mark.parametrize('m,count', [(1, 1), (3, 5), (4, 8), (5, 3)])
+def test_c3_dft_building_block_against_numpy(m, count):
+    """snfft_c3_dft alone: the forward shares one complex transform between two REAL rows (odd
+    row counts leave the last one alone), the adjoint writes planes or interleaved complex128."""
+    import ctypes as C
+    from snfft_b200 import _native as N
+    size = 3 ** m
+    rng = np.random.default_rng(10 * m + count)
+    f = rng.standard_normal((count, size))
+    freq = rng.choice(size, size=min(size, 7), replace=False).astype(np.int32)
+    digits = np.array([[(e // 3 ** (m - 1 - a)) % 3 for a in range(m)] for e in range(size)])   # first letter most significant
+    E = np.exp(2j * np.pi * (digits @ digits.T % 3) / 3.0)                                        # omega^{k.o}
+    fd, qd = torch.from_numpy(f).cuda(), torch.from_numpy(freq).cuda()
+    re = torch.full((count, len(freq)), float('nan'), dtype=torch.float64, device='cuda')
+    im = torch.full_like(re, float('nan'))
+    N.check(N.lib.snfft_c3_dft(m, N.ptr(fd), None, N.ptr(qd), len(freq), count, N.ptr(re), N.ptr(im), 0, None))
+    want = f @ E[:, freq]
+    got = torch.complex(re, im).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+    # adjoint: out[o] = sum_k in[k] omega^{-k.o}
+    wantT = want @ E[freq, :].conj()
+    ore = torch.empty((count, size), dtype=torch.float64, device='cuda')
+    oim = torch.empty_like(ore)
+    N.check(N.lib.snfft_c3_dft(m, N.ptr(re), N.ptr(im), N.ptr(qd), len(freq), count, N.ptr(ore), N.ptr(oim), 1, None))
+    assert np.abs(torch.complex(ore, oim).cpu().numpy() - wantT).max() < 1e-12 * np.abs(wantT).max()
+    both = torch.empty((count, size), dtype=torch.complex128, device='cuda')
+    N.check(N.lib.snfft_c3_dft(m, N.ptr(re), N.ptr(im), N.ptr(qd), len(freq), count, N.ptr(both), None, 1, None))
+    assert torch.equal(both, torch.complex(ore, oim))
+    # interleaved complex128 on both sides
+    spec = torch.empty((count, len(freq)), dtype=torch.complex128, device='cuda')
+    N.check(N.lib.snfft_c3_dft(m, N.ptr(fd), None, N.ptr(qd), len(freq), count, N.ptr(spec), None, 0, None))
+    assert torch.equal(spec, torch.complex(re, im))
+    N.check(N.lib.snfft_c3_dft(m, N.ptr(spec), None, N.ptr(qd), len(freq), count, N.ptr(both), None, 1, None))
+    assert torch.equal(both, torch.complex(ore, oim))
