@@ -320,8 +320,9 @@ def run_coset_split(n, rank, world, local, steps, warmup, barrier, peak):
 def run_wreath(local, peak):
     """BASELINE configs[3]: the C3 wr S8 (2x2 cube) transform of a random value function at one of
     the top irreps the reference names in code, (2,3,3)/((1,1),(1,1,1),(2,1)), D = 1120
-    (test_wreath.py:53-54).  Stage 1 = character sums over the orientations (radix-3 DFT kernel,
-    HBM bound: 8 |G| bytes read + 16 n! N written), stage 2 = gather + fp64 DMMA GEMM."""
+    (test_wreath.py:53-54).  Stage 1 = character sums over the orientations (C_3^7 DFT kernel,
+    algorithmic bytes 8 |G| read + 16 n! N written), stage 2 = the sums over the Young subgroup per
+    coset pair (fused gather kernel at this block size; gather + fp64 DMMA GEMM for large blocks)."""
     import torch
     from snfft_b200.wreath import WreathPlan
     dev = torch.device('cuda', local)

@@ -1566,7 +1566,7 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     std::vector<std::vector<std::vector<int>>> seg_perms(3);
     std::vector<std::vector<double>> seg_mats(3);  // [a_k!][d_k * d_k] on the host
     std::vector<int> seg_dim(3, 1);
-    int nontrivial = 0, only = -1;
+    int nontrivial = 0;
     double* single_dev = nullptr;
     for (int k = 0; k < 3; ++k) {
       const int a = alpha[k];
@@ -1578,7 +1578,6 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
         continue;
       }
       ++nontrivial;
-      only = k;
     }
     w->nH = (int64_t)seg_perms[0].size() * seg_perms[1].size() * seg_perms[2].size();
     if (w->N * w->nH != w->nfact) throw std::runtime_error("coset count times subgroup order != n!");
@@ -1624,7 +1623,6 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     w->D = w->N * w->block;
     const int64_t bb = w->block * w->block;
     if (nontrivial == 1) {
-      (void)only;
       w->R = single_dev;
     } else {
       std::vector<double> R((size_t)w->nH * bb);

@@ -403,11 +403,6 @@ __device__ unsigned long long g_phase_cycles[32];
 #define SNFFT_PH(i)
 #endif
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                "l"(gsrc)
@@ -1327,17 +1322,26 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
 // D consecutive base-3 digits (strides s, 3s, .. of the grid) transformed in registers: a 3^D-point
 // DFT per thread, D radix-3 stages on compile-time indices, one shared-memory round trip.
 // OUT = 0: back to shared memory; 1: straight to the global output planes (the last pass of the
-// adjoint); 2: the same as interleaved complex128 (one 16-byte store per point).
-template <int D, bool INV, int OUT>
+// adjoint); 2: the same as interleaved complex128 (one 16-byte store per point).  FROM_GLOBAL: the
+// points come from two real input rows (ga -> real part, gb -> imaginary part or null: zero) - the
+// first pass of the forward transform.
+template <int D, bool INV, int OUT, bool FROM_GLOBAL = false>
 __device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __restrict__ im, int base, int s,
-                                          double* __restrict__ gre, double* __restrict__ gim) {
+                                          double* __restrict__ gre, double* __restrict__ gim,
+                                          const double* __restrict__ ga = nullptr,
+                                          const double* __restrict__ gb = nullptr) {
   constexpr int P = D == 1 ? 3 : (D == 2 ? 9 : 27);
   const double h = INV ? -0.8660254037844386467637231707529 : 0.8660254037844386467637231707529;  // +-sqrt(3)/2
   double xr[P], xi[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
-    xr[j] = re[base + j * s];
-    xi[j] = im[base + j * s];
+    if (FROM_GLOBAL) {
+      xr[j] = ga[base + j * s];
+      xi[j] = gb ? gb[base + j * s] : 0.0;
+    } else {
+      xr[j] = re[base + j * s];
+      xi[j] = im[base + j * s];
+    }
   }
 #pragma unroll
   for (int dg = 0; dg < D; ++dg) {
@@ -1392,10 +1396,20 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
   double* im = grid + size;
   const int64_t sig = INV ? (int64_t)blockIdx.x : 2 * (int64_t)blockIdx.x;
   const bool second = !INV && sig + 1 < count;
+  int top = 0;  // digits already transformed on the way in (forward)
   if (!INV) {
-    for (int e = threadIdx.x; e < size; e += kDftThreads) {
-      re[e] = in_re[sig * size + e];
-      im[e] = second ? in_re[(sig + 1) * size + e] : 0.0;
+    // the top one or two digits straight from global memory: lanes run along the low digits, so
+    // the strided points of a thread are coalesced across the warp, and the grid is written once
+    // instead of written and read back (0.353 -> 0.331 ms for the cube)
+    top = m >= 2 ? 2 : 1;
+    const int pts = top == 2 ? 9 : 3, stride = size / pts;
+    const double* ga = in_re + sig * size;
+    const double* gb = second ? in_re + (sig + 1) * size : nullptr;
+    for (int t = threadIdx.x; t < stride; t += kDftThreads) {
+      if (top == 2)
+        c3_digits<2, INV, 0, true>(re, im, t, stride, nullptr, nullptr, ga, gb);
+      else
+        c3_digits<1, INV, 0, true>(re, im, t, stride, nullptr, nullptr, ga, gb);
     }
   } else {
     for (int e = threadIdx.x; e < size; e += kDftThreads) re[e] = im[e] = 0.0;
@@ -1422,8 +1436,9 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
   double* gre = INTERLEAVED ? out_re + 2 * sig * size : out_re + sig * size;
   double* gim = INTERLEAVED ? nullptr : out_im + sig * size;
   int done = 0, stride = 1;
-  while (done < m) {
-    const int dg = m - done >= 2 ? 2 : 1;
+  const int low = m - top;  // digits left for the passes over shared memory
+  while (done < low) {
+    const int dg = low - done >= 2 ? 2 : 1;
     const int pts = dg == 2 ? 9 : 3;
     const bool to_global = INV && done + dg == m;
     for (int t = threadIdx.x; t < size / pts; t += kDftThreads) {

@@ -297,3 +297,23 @@ def test_c3_dft_building_block_against_numpy(m, count):
     assert torch.equal(spec, torch.complex(re, im))
     N.check(N.lib.snfft_c3_dft(m, N.ptr(spec), None, N.ptr(qd), len(freq), count, N.ptr(both), None, 1, None))
     assert torch.equal(both, torch.complex(ore, oim))
+
+
+def test_cube_inverse_small_blocks_against_sampled_inverse():
+    """The wreath inverse at a cube irrep with small blocks (N = 560 cosets, b = 2: F-major adjoint
+    of stage 2, interleaved F, complex128 output) against the sampled inverse, an independent
+    evaluation of d tr(rho(g)^H f_hat) / |G| that the oracle tests pin."""
+    alpha, parts = (2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))
+    wp = WreathPlan(alpha, parts)
+    f = torch.randn((40320, 2187), dtype=torch.float64, device='cuda',
+                    generator=torch.Generator(device='cuda').manual_seed(91))
+    fh = wp.forward(f)
+    fused = wp.inverse(fh)
+    rng = random.Random(5)
+    sn = list(itertools.islice(itertools.permutations(range(1, 9)), 0, 40320, 4001))
+    elements = [(tuple(int(v) for v in wp.oris[rng.randrange(2187)]), rng.choice(sn)) for _ in range(6)]
+    want = wp.inverse_at(fh, elements)
+    lex = {p: i for i, p in enumerate(itertools.permutations(range(1, 9)))}
+    ori_index = {tuple(int(v) for v in o): i for i, o in enumerate(wp.oris.tolist())}
+    got = torch.stack([fused[lex[s], ori_index[o]] for o, s in elements])
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-12
