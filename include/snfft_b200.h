@@ -259,6 +259,14 @@ int snfft_wreath_forward(snfft_wreath* plan, const double* f_dev, double* out_re
  * written to out_re_dev as interleaved complex128 [n!][orientations] (16-byte aligned). */
 int snfft_wreath_inverse(snfft_wreath* plan, const double* fhat_re_dev, const double* fhat_im_dev,
                          double* out_re_dev, double* out_im_dev, void* stream);
+/* The same at `count` sampled group elements in ONE launch (cube_ift.py:56-67 per state, the
+ * consumer-facing form of compute_policy.py:66-88): element j = (orientation with index
+ * ori_index_dev[j] on the plan's orientation axis, permutation with lexicographic rank
+ * sigma_rank_dev[j] in perm2.sn order); out planes double[count].  Elements out of range give NaN.
+ * Reads the plan's tables only (no workspace: safe next to a running transform of the same plan). */
+int snfft_wreath_inverse_at(snfft_wreath* plan, const double* fhat_re_dev, const double* fhat_im_dev,
+                            const int64_t* sigma_rank_dev, const int32_t* ori_index_dev, int64_t count,
+                            double* out_re_dev, double* out_im_dev, void* stream);
 
 /* ---- Building blocks of the wreath-product transform (wreath.py / multi.py / cube_ft.py) -------
  * C[m,n] = A[m,k] B[k,n], fp64 row-major device matrices, on the DMMA tensor pipe

@@ -80,6 +80,7 @@ SIGNATURES = {
     "snfft_wreath_dims": (C.c_int, [_p, _p]),
     "snfft_wreath_forward": (C.c_int, [_p, _p, _p, _p, _p]),
     "snfft_wreath_inverse": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "snfft_wreath_inverse_at": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, _p, _p, _p]),
     "snfft_dgemm": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int64, _p]),
     "snfft_c3_dft": (C.c_int, [C.c_int, _p, _p, _p, C.c_int, C.c_int64, _p, _p, C.c_int, _p]),
     "snfft_gather": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int, _p]),

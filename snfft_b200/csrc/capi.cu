@@ -1778,6 +1778,22 @@ int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const doubl
   });
 }
 
+int snfft_wreath_inverse_at(snfft_wreath* w, const double* fhat_re_dev, const double* fhat_im_dev,
+                            const int64_t* sigma_rank_dev, const int32_t* ori_index_dev, int64_t count,
+                            double* out_re_dev, double* out_im_dev, void* stream) {
+  return guarded([&] {
+    if (!w || !fhat_re_dev || !fhat_im_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null argument");
+    if (count < 0) throw InvalidArg("count must be >= 0");
+    if (count > 0 && (!sigma_rank_dev || !ori_index_dev)) throw InvalidArg("null state list");
+    DeviceGuard guard(w->device);
+    // reads the plan's tables only: no workspace, no lock
+    CUDA_OK(launch_wreath_inverse_at(w->m, (int)w->N, (int)w->block, (int)w->nH, w->nfact, (int)w->n_ori, w->inv_idx, w->R,
+                                     fhat_re_dev, fhat_im_dev, w->freq, sigma_rank_dev, ori_index_dev, count,
+                                     (double)w->D / ((double)w->nfact * (double)w->n_ori), out_re_dev, out_im_dev,
+                                     (cudaStream_t)stream));
+  });
+}
+
 int snfft_c3_dft(int m, const double* in_re_dev, const double* in_im_dev, const int32_t* freq_dev, int nfreq,
                  int64_t count, double* out_re_dev, double* out_im_dev, int inverse, void* stream) {
   return guarded([&] {

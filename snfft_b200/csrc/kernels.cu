@@ -1836,6 +1836,65 @@ wreath_stage2_adjoint_kernel(int nH, int64_t total, const int64_t* __restrict__ 
   }
 }
 
+// Sampled wreath inverse (cube_ift.py:56-67 per state, the consumer of compute_policy.py:66-88):
+//   f(o, sigma) = D / |G| * sum_i conj(chi_i(o)) <block(i, j_i), R[h_i]>,   sigma = t_i h_i t_{j_i}^-1,
+// i.e. the F-major adjoint of stage 2 at the row sigma followed by ONE term of the adjoint DFT.
+// One CTA = one state; threads run over the cosets i.  States out of range give NaN.
+__global__ void __launch_bounds__(256)
+wreath_inverse_at_kernel(int m, int N, int b, int nH, int64_t nfact, int n_ori, const int64_t* __restrict__ inv_idx,
+                         const double* __restrict__ R, const double* __restrict__ Mre,
+                         const double* __restrict__ Mim, const int32_t* __restrict__ freq,
+                         const int64_t* __restrict__ sigma, const int32_t* __restrict__ ori, double scale,
+                         double* __restrict__ out_re, double* __restrict__ out_im) {
+  __shared__ double part[2][8];
+  const int64_t s = sigma[blockIdx.x];
+  const int o = ori[blockIdx.x];
+  const bool ok = s >= 0 && s < nfact && o >= 0 && o < n_ori;
+  const int64_t D = (int64_t)N * b;
+  const int bb = b * b;
+  double ar = 0.0, ai = 0.0;
+  for (int i = threadIdx.x; ok && i < N; i += 256) {
+    const uint64_t e = (uint64_t)inv_idx[s * N + i];  // (i N + j) nH + h
+    const uint64_t pair = e / (uint64_t)nH;
+    const int h = (int)(e - pair * (uint64_t)nH);
+    const int64_t j = (int64_t)(pair - (uint64_t)i * (uint64_t)N);
+    double er = 0.0, ei = 0.0;
+    for (int q = 0; q < bb; ++q) {
+      const int a = q / b, c = q - a * b;
+      const double r = R[h * bb + q];
+      er = fma(Mre[((int64_t)i * b + a) * D + j * b + c], r, er);
+      ei = fma(Mim[((int64_t)i * b + a) * D + j * b + c], r, ei);
+    }
+    int ex = 0;  // k_i . o over the base-3 digits
+    for (int d = 0, k = freq[i], oo = o; d < m; ++d, k /= 3, oo /= 3) ex += (k % 3) * (oo % 3);
+    ex %= 3;
+    // conj(chi) = omega^{-ex}
+    const double cr = ex == 0 ? 1.0 : -0.5;
+    const double ci = ex == 0 ? 0.0 : (ex == 1 ? -0.8660254037844386467637231707529 : 0.8660254037844386467637231707529);
+    ar += er * cr - ei * ci;
+    ai += er * ci + ei * cr;
+  }
+  for (int w = 16; w > 0; w >>= 1) {
+    ar += __shfl_down_sync(0xffffffffu, ar, w);
+    ai += __shfl_down_sync(0xffffffffu, ai, w);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    part[0][threadIdx.x >> 5] = ar;
+    part[1][threadIdx.x >> 5] = ai;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sr = 0.0, si = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      sr += part[0][w];
+      si += part[1][w];
+    }
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    out_re[blockIdx.x] = ok ? scale * sr : nan;
+    out_im[blockIdx.x] = ok ? scale * si : nan;
+  }
+}
+
 __global__ void transpose_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t rows, int64_t cols) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
@@ -2263,6 +2322,18 @@ cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, dou
     wreath_permute_kernel<true><<<grid_for(D * D), 256, 0, stream>>>(N, b, mat, planes, scale);
   else
     wreath_permute_kernel<false><<<grid_for(D * D), 256, 0, stream>>>(N, b, mat, planes, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact, int n_ori, const int64_t* inv_idx,
+                                     const double* R, const double* Mre, const double* Mim, const int32_t* freq,
+                                     const int64_t* sigma, const int32_t* ori, int64_t count, double scale,
+                                     double* out_re, double* out_im, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  if (count > 0x7fffffffLL) return cudaErrorInvalidValue;
+  LaunchScope scope(kKindOther, stream);
+  wreath_inverse_at_kernel<<<(unsigned)count, 256, 0, stream>>>(m, N, b, nH, nfact, n_ori, inv_idx, R, Mre, Mim, freq,
+                                                               sigma, ori, scale, out_re, out_im);
   return cudaGetLastError();
 }
 

@@ -75,6 +75,11 @@ cudaError_t launch_wreath_index(int n, int N, int nH, const int8_t* T, const int
                                 int64_t* idx, int64_t* inv_idx, cudaStream_t stream);
 cudaError_t launch_wreath_permute(int N, int b, double* mat, double* planes, double scale, bool to_matrix,
                                   cudaStream_t stream);
+// f(o_j, sigma_j) for `count` sampled states: sigma as lexicographic ranks, o as orientation indices
+cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact, int n_ori, const int64_t* inv_idx,
+                                     const double* R, const double* Mre, const double* Mim, const int32_t* freq,
+                                     const int64_t* sigma, const int32_t* ori, int64_t count, double scale,
+                                     double* out_re, double* out_im, cudaStream_t stream);
 cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream);
 cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream);
 // stage 2 fused for small blocks (b*b in {1,4,9,16}, many cosets): gather + block sums + placement in one kernel

@@ -466,6 +466,31 @@ class WreathPlan:
         for every j the coset i of sigma t_j is known, so the trace runs over N blocks, not N^2."""
         import torch
         dev = fhat.device
+        if self._c is not None:
+            # one launch for all states (snfft_wreath_inverse_at): sigma as lexicographic ranks, the
+            # orientation as its index on the plan's axis (base-3 number of the first dft_m letters)
+            sig = _lex_ranks(np.array([s for _, s in elements], dtype=np.int64).reshape(-1, self.n))
+            o = np.array([t for t, _ in elements], dtype=np.int64).reshape(-1, self.n)
+            if self.mode == 'zero_sum' and (o.sum(axis=1) % 3).any():
+                raise ValueError('orientation tuples must sum to 0 mod 3 on this plan')
+            oi = (o[:, :self.dft_m] @ (3 ** np.arange(self.dft_m - 1, -1, -1))).astype(np.int32)
+            fre, fim = fhat.real.contiguous(), fhat.imag.contiguous()
+            sd, od = torch.from_numpy(sig).to(dev), torch.from_numpy(oi).to(dev)
+            re = torch.empty(len(elements), dtype=torch.float64, device=dev)
+            im = torch.empty_like(re)
+            with torch.cuda.device(self.device):
+                N.check(N.lib.snfft_wreath_inverse_at(self._c, N.ptr(fre), N.ptr(fim), N.ptr(sd), N.ptr(od), len(elements),
+                                                      N.ptr(re), N.ptr(im),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            return torch.complex(re, im)
+        return self.inverse_at_host(fhat, elements)
+
+    def inverse_at_host(self, fhat, elements):
+        """The same values with the coset search driven from the host, one state at a time: the
+        path of plans without a C handle (general C_m, arbitrary orientation lists) and an
+        independent cross-check of the kernel."""
+        import torch
+        dev = fhat.device
         b, N_ = self.block, self.N
         T = np.array(self.reps, dtype=np.int64)
         index = {tuple(t): i for i, t in enumerate(self.reps)}

@@ -168,6 +168,8 @@ def test_sampled_wreath_inverse_against_oracle(ci):
     got = wp.inverse_at(torch.from_numpy(fhat).cuda(), [(oris[q], group[s]) for s, q in picks]).cpu().numpy()
     ref = np.array([want[s, q] for s, q in picks])
     assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    host = wp.inverse_at_host(torch.from_numpy(fhat).cuda(), [(oris[q], group[s]) for s, q in picks]).cpu().numpy()
+    assert np.abs(host - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
     # and the dense device inverse agrees with the sampled one on the cube-sized path too
     dense = wp.inverse(torch.from_numpy(fhat).cuda()).cpu().numpy()
     assert np.abs(dense - want).max() < 1e-10 * max(1.0, np.abs(want).max())
@@ -312,7 +314,9 @@ def test_cube_inverse_small_blocks_against_sampled_inverse():
     rng = random.Random(5)
     sn = list(itertools.islice(itertools.permutations(range(1, 9)), 0, 40320, 4001))
     elements = [(tuple(int(v) for v in wp.oris[rng.randrange(2187)]), rng.choice(sn)) for _ in range(6)]
-    want = wp.inverse_at(fh, elements)
+    want = wp.inverse_at_host(fh, elements)
+    kernel = wp.inverse_at(fh, elements)                      # snfft_wreath_inverse_at: one launch
+    assert ((kernel - want).abs().max() / want.abs().max()).item() < 1e-12
     lex = {p: i for i, p in enumerate(itertools.permutations(range(1, 9)))}
     ori_index = {tuple(int(v) for v in o): i for i, o in enumerate(wp.oris.tolist())}
     got = torch.stack([fused[lex[s], ori_index[o]] for o, s in elements])

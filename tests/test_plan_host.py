@@ -76,6 +76,9 @@ def test_host_only_plan_refuses_device_work():
     assert N.lib.snfft_wreath_create(4, N.ptr(np.array([1, 1, 1], dtype=np.int32)), N.ptr(parts), 0, -1,
                                      C.byref(C.c_void_p())) == 1
     assert N.lib.snfft_c3_dft(9, N.ptr(buf), None, N.ptr(perms), 1, 1, N.ptr(buf), N.ptr(buf), 0, None) == 1
+    # null plan / null state list: statuses, not crashes
+    assert N.lib.snfft_wreath_inverse_at(None, N.ptr(buf), N.ptr(buf), None, None, 0, N.ptr(buf), N.ptr(buf), None) == 1
+    assert N.lib.snfft_wreath_inverse(None, N.ptr(buf), N.ptr(buf), N.ptr(buf), None, None) == 1
 
 
 @pytest.mark.parametrize('n', range(1, 11))
