@@ -118,6 +118,35 @@ class ClockSampler:
                 'samples': len(sm), 'samples_in_timed_region': in_region, 'reasons': sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned
+    host buffers of the e2e leg are allocated (first touch then places them on that node): with one
+    process per GPU the host<->device copies of all ranks otherwise share one socket's memory and
+    the inter-socket link.  Returns the node, or None when the topology is not exposed."""
+    if os.environ.get('SNFFT_NO_NUMA_BIND'):
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
+            cpus = set()
+            for part in fh.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def run_reference(args, rank, world):
     """The reference arm: the oracle port of the reference's CPU algorithms on all host cores."""
     if rank != 0:
@@ -394,6 +423,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_node = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -571,7 +601,7 @@ def main():
             'config_detail': {'elements_per_step': elements_per_step, 'directions_per_step': 2,
                               'order': 'coset-major',
                               'parallelism': f'batch-replicas x{world}' if world > 1 else 'single GPU',
-                              'round_trip_rel_err': err},
+                              'round_trip_rel_err': err, 'host_numa_node_rank0': numa_node},
             'roofline': roofline,
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'elements/s',
