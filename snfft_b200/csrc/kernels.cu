@@ -1379,6 +1379,61 @@ __device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __res
 
 constexpr int kDftThreads = 128;
 
+// Task order of the radix-9 pass over digits (2, 3) (stride 9): task (hi, lo) starts at
+// 81 hi + lo, so with lanes = consecutive (hi, lo) the 16 lanes of a half warp hit only 9 distinct
+// bank pairs (81 = 1 mod 16) and every shared-memory access of the pass takes two wavefronts (ncu:
+// 36 % of the kernel's wavefronts were conflicts).  The tasks are regrouped at compile time so that
+// the start addresses of each aligned group of 16 are distinct mod 16 wherever the counts allow
+// (-1 = idle slot).  m = digits of the grid, 4..8.
+struct C3Order {
+  int n;
+  short base[768];
+};
+constexpr C3Order make_c3_order(int m) {
+  C3Order T{};
+  int size = 1;
+  for (int a = 0; a < m; ++a) size *= 3;
+  const int H = size / 81, tasks = 9 * H, groups = (tasks + 15) / 16;
+  bool lane_used[48][16] = {};
+  int filled[48] = {};
+  for (int i = 0; i < 768; ++i) T.base[i] = -1;
+  short left[768] = {};
+  int nleft = 0;
+  for (int hi = 0; hi < H; ++hi)
+    for (int lo = 0; lo < 9; ++lo) {
+      const int base = 81 * hi + lo, r = base & 15;
+      int g = 0;
+      while (g < groups && lane_used[g][r]) ++g;
+      if (g < groups) {
+        lane_used[g][r] = true;
+        T.base[g * 16 + filled[g]++] = (short)base;
+      } else {
+        left[nleft++] = (short)base;
+      }
+    }
+  for (int i = 0, g = 0; i < nleft; ++i) {  // what did not fit: any free slot (a 2-way conflict there)
+    while (filled[g] == 16) ++g;
+    T.base[g * 16 + filled[g]++] = left[i];
+  }
+  T.n = groups * 16;
+  return T;
+}
+__device__ constexpr C3Order kC3Order4 = make_c3_order(4);
+__device__ constexpr C3Order kC3Order5 = make_c3_order(5);
+__device__ constexpr C3Order kC3Order6 = make_c3_order(6);
+__device__ constexpr C3Order kC3Order7 = make_c3_order(7);
+__device__ constexpr C3Order kC3Order8 = make_c3_order(8);
+__device__ __forceinline__ const C3Order* c3_order(int m) {
+  switch (m) {
+    case 4: return &kC3Order4;
+    case 5: return &kC3Order5;
+    case 6: return &kC3Order6;
+    case 7: return &kC3Order7;
+    case 8: return &kC3Order8;
+    default: return nullptr;
+  }
+}
+
 // Forward: the input rows are REAL, so one complex transform serves TWO rows: z = f(s1,.) + i f(s2,.),
 // Z = DFT(z), and F_1(k) = (Z(k) + conj Z(-k)) / 2, F_2(k) = (Z(k) - conj Z(-k)) / 2i.  One CTA =
 // one pair of rows; half the arithmetic and half the shared-memory traffic per row.  The adjoint
@@ -1441,9 +1496,17 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
     const int dg = low - done >= 2 ? 2 : 1;
     const int pts = dg == 2 ? 9 : 3;
     const bool to_global = INV && done + dg == m;
-    for (int t = threadIdx.x; t < size / pts; t += kDftThreads) {
-      const int hi = t / stride, lo = t - hi * stride;
-      const int base = hi * pts * stride + lo;
+    const C3Order* order = dg == 2 && stride == 9 ? c3_order(m) : nullptr;
+    const int ntask = order ? order->n : size / pts;
+    for (int t = threadIdx.x; t < ntask; t += kDftThreads) {
+      int base;
+      if (order) {
+        base = order->base[t];
+        if (base < 0) continue;
+      } else {
+        const int hi = t / stride, lo = t - hi * stride;
+        base = hi * pts * stride + lo;
+      }
       if (dg == 2) {
         if (to_global)
           c3_digits<2, INV, INTERLEAVED ? 2 : 1>(re, im, base, stride, gre, gim);
