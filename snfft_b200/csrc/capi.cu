@@ -1453,7 +1453,7 @@ struct snfft_wreath {
   int64_t N = 0, nH = 0, block = 0, D = 0, nfact = 0, n_ori = 0;
   int32_t* freq = nullptr;
   int64_t *idx = nullptr, *inv_idx = nullptr;
-  int64_t* idx_t = nullptr;                                // idx transposed to [h][pair] (fused stage 2), or null
+  int32_t* idx_t = nullptr;                                // idx transposed to [h][pair], 32-bit (fused stage 2), or null
   // alpha = (n, 0, 0) up to order: S_alpha = S_n, one coset, and stage 2 IS the S_n Fourier transform of
   // the character sum at the irrep `parts`: it runs through the Clausen-Baum levels (forward_impl)
   snfft_plan* sn_plan = nullptr;
@@ -1670,7 +1670,8 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     w->inv_idx = w->alloc<int64_t>((size_t)w->nfact * w->N);
     CUDA_OK(launch_wreath_index(n, (int)w->N, (int)w->nH, T_dev, Tinv_dev, H_dev, w->idx, w->inv_idx, nullptr));
     if (wreath_stage2_fits((int)w->N, (int)w->block, (int)w->nH)) {
-      w->idx_t = w->alloc<int64_t>((size_t)w->nfact * w->N);
+      if (w->nfact * w->N > 0x7fffffffLL) throw std::runtime_error("gather index does not fit 32 bits");
+      w->idx_t = w->alloc<int32_t>((size_t)w->nfact * w->N);
       CUDA_OK(launch_transpose_i64(w->idx, w->idx_t, w->N * w->N, w->nH, nullptr));
     }
     // ---- workspace ----

@@ -1828,7 +1828,7 @@ __global__ void wreath_permute_kernel(int N, int b, double* __restrict__ mat, do
 // GEMM + permute per plane.  One thread = one coset pair.
 template <int BB>
 __global__ void __launch_bounds__(256)
-wreath_stage2_kernel(int N, int b, int nH, const int64_t* __restrict__ idx_t, const double* __restrict__ R,
+wreath_stage2_kernel(int N, int b, int nH, const int32_t* __restrict__ idx_t, const double* __restrict__ R,
                      const double2* __restrict__ F, double* __restrict__ Mre, double* __restrict__ Mim) {
   extern __shared__ double Rs[];  // [nH][BB]
   for (int e = threadIdx.x; e < nH * BB; e += 256) Rs[e] = R[e];
@@ -1839,7 +1839,22 @@ wreath_stage2_kernel(int N, int b, int nH, const int64_t* __restrict__ idx_t, co
     double ar[BB], ai[BB];
 #pragma unroll
     for (int q = 0; q < BB; ++q) ar[q] = ai[q] = 0.0;
-    for (int h = 0; h < nH; ++h) {
+    // four independent gathers in flight per thread (the loop is latency-bound: ncu long scoreboard)
+    int h = 0;
+    for (; h + 4 <= nH; h += 4) {
+      double2 fv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fv[u] = F[idx_t[(int64_t)(h + u) * pairs + p]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < BB; ++q) {
+          const double r = Rs[(h + u) * BB + q];
+          ar[q] = fma(fv[u].x, r, ar[q]);
+          ai[q] = fma(fv[u].y, r, ai[q]);
+        }
+    }
+    for (; h < nH; ++h) {
       const double2 fv = F[idx_t[(int64_t)h * pairs + p]];
 #pragma unroll
       for (int q = 0; q < BB; ++q) {
@@ -1958,10 +1973,11 @@ wreath_inverse_at_kernel(int m, int N, int b, int nH, int64_t nfact, int n_ori, 
   }
 }
 
-__global__ void transpose_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int64_t rows, int64_t cols) {
+// the gather index transposed to [h][pair] and narrowed to 32 bits (n! N < 2^31 for every plan)
+__global__ void transpose_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t rows, int64_t cols) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
-    out[c * rows + r] = in[e];
+    out[c * rows + r] = (int32_t)in[e];
   }
 }
 
@@ -2400,7 +2416,7 @@ cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact,
   return cudaGetLastError();
 }
 
-cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream) {
+cudaError_t launch_transpose_i64(const int64_t* in, int32_t* out, int64_t rows, int64_t cols, cudaStream_t stream) {
   LaunchScope scope(kKindOther, stream);
   transpose_i64_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(in, out, rows, cols);
   return cudaGetLastError();
@@ -2411,7 +2427,7 @@ bool wreath_stage2_fits(int N, int b, int nH) {
   return (bb == 1 || bb == 4 || bb == 9 || bb == 16) && N >= 32 && (size_t)nH * bb * sizeof(double) <= 96 * 1024;
 }
 
-cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int64_t* idx_t, const int64_t* inv_idx,
+cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int32_t* idx_t, const int64_t* inv_idx,
                                  const double* R, double* F, double* Mre, double* Mim, double* blocks, bool inverse,
                                  cudaStream_t stream) {
   const int bb = b * b;

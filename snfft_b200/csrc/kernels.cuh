@@ -81,11 +81,11 @@ cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact,
                                      const int64_t* sigma, const int32_t* ori, int64_t count, double scale,
                                      double* out_re, double* out_im, cudaStream_t stream);
 cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream);
-cudaError_t launch_transpose_i64(const int64_t* in, int64_t* out, int64_t rows, int64_t cols, cudaStream_t stream);
+cudaError_t launch_transpose_i64(const int64_t* in, int32_t* out, int64_t rows, int64_t cols, cudaStream_t stream);  // narrows to 32 bits
 // stage 2 fused for small blocks (b*b in {1,4,9,16}, many cosets): gather + block sums + placement in one kernel
 bool wreath_stage2_fits(int N, int b, int nH);
 // F: interleaved complex128 [n!][N]; forward reads it through idx_t ([h][pair]), the adjoint writes it through inv_idx
-cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int64_t* idx_t, const int64_t* inv_idx,
+cudaError_t launch_wreath_stage2(int N, int b, int nH, int64_t nfact, const int32_t* idx_t, const int64_t* inv_idx,
                                  const double* R, double* F, double* Mre, double* Mim, double* blocks, bool inverse,
                                  cudaStream_t stream);  // blocks: 2 N^2 b^2 doubles of scratch (adjoint)
 
