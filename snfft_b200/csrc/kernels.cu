@@ -1326,7 +1326,7 @@ yor_kernel(int n, int d, const int32_t* __restrict__ partner, const double* __re
 // points come from two real input rows (ga -> real part, gb -> imaginary part or null: zero) - the
 // first pass of the forward transform.
 template <int D, bool INV, int OUT, bool FROM_GLOBAL = false>
-__device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __restrict__ im, int base, int s,
+__device__ __forceinline__ void c3_digits(double2* __restrict__ g, int base, int s,
                                           double* __restrict__ gre, double* __restrict__ gim,
                                           const double* __restrict__ ga = nullptr,
                                           const double* __restrict__ gb = nullptr) {
@@ -1339,8 +1339,9 @@ __device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __res
       xr[j] = ga[base + j * s];
       xi[j] = gb ? gb[base + j * s] : 0.0;
     } else {
-      xr[j] = re[base + j * s];
-      xi[j] = im[base + j * s];
+      const double2 v = g[base + j * s];
+      xr[j] = v.x;
+      xi[j] = v.y;
     }
   }
 #pragma unroll
@@ -1371,68 +1372,15 @@ __device__ __forceinline__ void c3_digits(double* __restrict__ re, double* __res
       gre[base + j * s] = xr[j];
       gim[base + j * s] = xi[j];
     } else {
-      re[base + j * s] = xr[j];
-      im[base + j * s] = xi[j];
+      g[base + j * s] = make_double2(xr[j], xi[j]);
     }
   }
 }
 
-constexpr int kDftThreads = 128;
-
-// Task order of the radix-9 pass over digits (2, 3) (stride 9): task (hi, lo) starts at
-// 81 hi + lo, so with lanes = consecutive (hi, lo) the 16 lanes of a half warp hit only 9 distinct
-// bank pairs (81 = 1 mod 16) and every shared-memory access of the pass takes two wavefronts (ncu:
-// 36 % of the kernel's wavefronts were conflicts).  The tasks are regrouped at compile time so that
-// the start addresses of each aligned group of 16 are distinct mod 16 wherever the counts allow
-// (-1 = idle slot).  m = digits of the grid, 4..8.
-struct C3Order {
-  int n;
-  short base[768];
-};
-constexpr C3Order make_c3_order(int m) {
-  C3Order T{};
-  int size = 1;
-  for (int a = 0; a < m; ++a) size *= 3;
-  const int H = size / 81, tasks = 9 * H, groups = (tasks + 15) / 16;
-  bool lane_used[48][16] = {};
-  int filled[48] = {};
-  for (int i = 0; i < 768; ++i) T.base[i] = -1;
-  short left[768] = {};
-  int nleft = 0;
-  for (int hi = 0; hi < H; ++hi)
-    for (int lo = 0; lo < 9; ++lo) {
-      const int base = 81 * hi + lo, r = base & 15;
-      int g = 0;
-      while (g < groups && lane_used[g][r]) ++g;
-      if (g < groups) {
-        lane_used[g][r] = true;
-        T.base[g * 16 + filled[g]++] = (short)base;
-      } else {
-        left[nleft++] = (short)base;
-      }
-    }
-  for (int i = 0, g = 0; i < nleft; ++i) {  // what did not fit: any free slot (a 2-way conflict there)
-    while (filled[g] == 16) ++g;
-    T.base[g * 16 + filled[g]++] = left[i];
-  }
-  T.n = groups * 16;
-  return T;
-}
-__device__ constexpr C3Order kC3Order4 = make_c3_order(4);
-__device__ constexpr C3Order kC3Order5 = make_c3_order(5);
-__device__ constexpr C3Order kC3Order6 = make_c3_order(6);
-__device__ constexpr C3Order kC3Order7 = make_c3_order(7);
-__device__ constexpr C3Order kC3Order8 = make_c3_order(8);
-__device__ __forceinline__ const C3Order* c3_order(int m) {
-  switch (m) {
-    case 4: return &kC3Order4;
-    case 5: return &kC3Order5;
-    case 6: return &kC3Order6;
-    case 7: return &kC3Order7;
-    case 8: return &kC3Order8;
-    default: return nullptr;
-  }
-}
+// threads per CTA, measured for the cube (3^7 grid, 243 radix-9 tasks per pass): the forward kernel is
+// fastest with all tasks of a pass in one round (0.300 -> 0.267 ms), the adjoint with two rounds of 128
+// (0.488 vs 0.582 ms with 256)
+constexpr int kDftThreadsFwd = 256, kDftThreadsAdj = 128;
 
 // Forward: the input rows are REAL, so one complex transform serves TWO rows: z = f(s1,.) + i f(s2,.),
 // Z = DFT(z), and F_1(k) = (Z(k) + conj Z(-k)) / 2, F_2(k) = (Z(k) - conj Z(-k)) / 2i.  One CTA =
@@ -1441,14 +1389,19 @@ __device__ __forceinline__ const C3Order* c3_order(int m) {
 // the nfreq scattered values and the last pass stores to global memory from registers (lanes run
 // along the low digits: coalesced).  INTERLEAVED: the output is complex128 in out_re instead of
 // two planes; in_im == nullptr: the adjoint's input is complex128 in in_re.
+//
+// The grid lives in shared memory as interleaved complex (double2): every point is ONE 16-byte
+// access, and the task starts of all passes (9 t, 81 hi + lo, ...) are distinct mod 8 within a
+// quarter warp, so the accesses are conflict-free.  (Two planes of doubles: the stride-9 pass hit 9
+// of 16 bank pairs per half warp; ncu counted 36 % / 29 % of the wavefronts of the forward / adjoint
+// kernel as bank conflicts.)
 template <bool INV, bool INTERLEAVED>
-__global__ void __launch_bounds__(kDftThreads)
+__global__ void __launch_bounds__(INV ? kDftThreadsAdj : kDftThreadsFwd)
 c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, const double* __restrict__ in_im,
               const int32_t* __restrict__ freq, int nfreq, double* __restrict__ out_re,
               double* __restrict__ out_im, double scale) {
-  extern __shared__ double grid[];
-  double* re = grid;
-  double* im = grid + size;
+  extern __shared__ double2 grid[];
+  constexpr int kDftThreads = INV ? kDftThreadsAdj : kDftThreadsFwd;
   const int64_t sig = INV ? (int64_t)blockIdx.x : 2 * (int64_t)blockIdx.x;
   const bool second = !INV && sig + 1 < count;
   int top = 0;  // digits already transformed on the way in (forward)
@@ -1462,12 +1415,12 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
     const double* gb = second ? in_re + (sig + 1) * size : nullptr;
     for (int t = threadIdx.x; t < stride; t += kDftThreads) {
       if (top == 2)
-        c3_digits<2, INV, 0, true>(re, im, t, stride, nullptr, nullptr, ga, gb);
+        c3_digits<2, INV, 0, true>(grid, t, stride, nullptr, nullptr, ga, gb);
       else
-        c3_digits<1, INV, 0, true>(re, im, t, stride, nullptr, nullptr, ga, gb);
+        c3_digits<1, INV, 0, true>(grid, t, stride, nullptr, nullptr, ga, gb);
     }
   } else {
-    for (int e = threadIdx.x; e < size; e += kDftThreads) re[e] = im[e] = 0.0;
+    for (int e = threadIdx.x; e < size; e += kDftThreads) grid[e] = make_double2(0.0, 0.0);
     __syncthreads();
     for (int i = threadIdx.x; i < nfreq; i += kDftThreads) {
       double vr, vi;
@@ -1479,8 +1432,7 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
         vr = v.x;
         vi = v.y;
       }
-      re[freq[i]] = scale * vr;
-      im[freq[i]] = scale * vi;
+      grid[freq[i]] = make_double2(scale * vr, scale * vi);
     }
   }
   __syncthreads();
@@ -1496,27 +1448,19 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
     const int dg = low - done >= 2 ? 2 : 1;
     const int pts = dg == 2 ? 9 : 3;
     const bool to_global = INV && done + dg == m;
-    const C3Order* order = dg == 2 && stride == 9 ? c3_order(m) : nullptr;
-    const int ntask = order ? order->n : size / pts;
-    for (int t = threadIdx.x; t < ntask; t += kDftThreads) {
-      int base;
-      if (order) {
-        base = order->base[t];
-        if (base < 0) continue;
-      } else {
-        const int hi = t / stride, lo = t - hi * stride;
-        base = hi * pts * stride + lo;
-      }
+    for (int t = threadIdx.x; t < size / pts; t += kDftThreads) {
+      const int hi = t / stride, lo = t - hi * stride;
+      const int base = hi * pts * stride + lo;
       if (dg == 2) {
         if (to_global)
-          c3_digits<2, INV, INTERLEAVED ? 2 : 1>(re, im, base, stride, gre, gim);
+          c3_digits<2, INV, INTERLEAVED ? 2 : 1>(grid, base, stride, gre, gim);
         else
-          c3_digits<2, INV, 0>(re, im, base, stride, nullptr, nullptr);
+          c3_digits<2, INV, 0>(grid, base, stride, nullptr, nullptr);
       } else {
         if (to_global)
-          c3_digits<1, INV, INTERLEAVED ? 2 : 1>(re, im, base, stride, gre, gim);
+          c3_digits<1, INV, INTERLEAVED ? 2 : 1>(grid, base, stride, gre, gim);
         else
-          c3_digits<1, INV, 0>(re, im, base, stride, nullptr, nullptr);
+          c3_digits<1, INV, 0>(grid, base, stride, nullptr, nullptr);
       }
     }
     __syncthreads();
@@ -1532,17 +1476,17 @@ c3_dft_kernel(int m, int size, int64_t count, const double* __restrict__ in_re, 
         r /= 3;
         kn += (d == 0 ? 0 : 3 - d) * p;
       }
-      const double zr = re[k], zi = im[k], wr = re[kn], wi = im[kn];
+      const double2 z = grid[k], w = grid[kn];
       if (INTERLEAVED) {
         double2* o = reinterpret_cast<double2*>(out_re);
-        o[sig * nfreq + i] = make_double2(0.5 * (zr + wr), 0.5 * (zi - wi));
-        if (second) o[(sig + 1) * nfreq + i] = make_double2(0.5 * (zi + wi), 0.5 * (wr - zr));
+        o[sig * nfreq + i] = make_double2(0.5 * (z.x + w.x), 0.5 * (z.y - w.y));
+        if (second) o[(sig + 1) * nfreq + i] = make_double2(0.5 * (z.y + w.y), 0.5 * (w.x - z.x));
       } else {
-        out_re[sig * nfreq + i] = 0.5 * (zr + wr);
-        out_im[sig * nfreq + i] = 0.5 * (zi - wi);
+        out_re[sig * nfreq + i] = 0.5 * (z.x + w.x);
+        out_im[sig * nfreq + i] = 0.5 * (z.y - w.y);
         if (second) {
-          out_re[(sig + 1) * nfreq + i] = 0.5 * (zi + wi);
-          out_im[(sig + 1) * nfreq + i] = 0.5 * (wr - zr);
+          out_re[(sig + 1) * nfreq + i] = 0.5 * (z.y + w.y);
+          out_im[(sig + 1) * nfreq + i] = 0.5 * (w.x - z.x);
         }
       }
     }
@@ -2473,16 +2417,16 @@ cudaError_t launch_c3_dft(int m, const double* in_re, const double* in_im, const
   const size_t smem = 2 * (size_t)size * sizeof(double);
   LaunchScope scope(kKindOther, stream);
   if (!inverse && out_im)
-    c3_dft_kernel<false, false><<<(unsigned)((count + 1) / 2), kDftThreads, smem, stream>>>(
+    c3_dft_kernel<false, false><<<(unsigned)((count + 1) / 2), kDftThreadsFwd, smem, stream>>>(
         m, size, count, in_re, in_im, freq, nfreq, out_re, out_im, scale);
   else if (!inverse)
-    c3_dft_kernel<false, true><<<(unsigned)((count + 1) / 2), kDftThreads, smem, stream>>>(
+    c3_dft_kernel<false, true><<<(unsigned)((count + 1) / 2), kDftThreadsFwd, smem, stream>>>(
         m, size, count, in_re, in_im, freq, nfreq, out_re, out_im, scale);
   else if (out_im)
-    c3_dft_kernel<true, false><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, count, in_re, in_im, freq,
+    c3_dft_kernel<true, false><<<(unsigned)count, kDftThreadsAdj, smem, stream>>>(m, size, count, in_re, in_im, freq,
                                                                                nfreq, out_re, out_im, scale);
   else
-    c3_dft_kernel<true, true><<<(unsigned)count, kDftThreads, smem, stream>>>(m, size, count, in_re, in_im, freq,
+    c3_dft_kernel<true, true><<<(unsigned)count, kDftThreadsAdj, smem, stream>>>(m, size, count, in_re, in_im, freq,
                                                                               nfreq, out_re, out_im, scale);
   return cudaGetLastError();
 }
