@@ -1049,8 +1049,8 @@ phase_kernel(PhaseDev P, PhaseLaunch Lp, double* __restrict__ xside, double* __r
 template <bool INV>
 __global__ void __launch_bounds__(256)
 p1_inplace_kernel(P1Dev P, double* __restrict__ xside, int64_t lgroups) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < P.nitems; item += (int64_t)gridDim.x * 8) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int64_t item = (int64_t)blockIdx.x * nwarps + warp; item < P.nitems; item += (int64_t)gridDim.x * nwarps) {
     const P1Entry e = P.entries[P.item_entry[item]];  // entries are sorted by sigma: warps of a CTA share code
     const int c = (int)(item - e.item_off) * 32 + lane;
     if (c >= e.d) continue;
@@ -2212,14 +2212,23 @@ cudaError_t launch_phase(const PhaseDev& P, const int32_t* panel_groups, const i
 cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int64_t lgroups, bool inverse,
                               int num_sms, cudaStream_t stream) {
   if (lgroups <= 0) return cudaSuccess;
-  auto grid_for = [&](int64_t items) {
+  // the in-place programs hold up to 36 rows in registers (172..184 registers per thread): small CTAs
+  // pack more warps onto an SM (register allocation is per CTA): S_12 p1 time 7.29 ms with 256
+  // threads, 7.16 with 128, 7.13 with 64 or 32.  SNFFT_P1_THREADS overrides.
+  int p1_threads = 64;
+  if (const char* env = std::getenv("SNFFT_P1_THREADS")) {
+    const int want = std::atoi(env);
+    if (want == 32 || want == 64 || want == 128 || want == 256) p1_threads = want;
+  }
+  auto grid_for_warps = [&](int64_t items, int warps) {
     int64_t gy = lgroups < 64 ? lgroups : 64;
-    int64_t gx = (items + 7) / 8;
-    const int64_t want = 32LL * num_sms;
+    int64_t gx = (items + warps - 1) / warps;
+    const int64_t want = 32LL * num_sms * 8 / warps;
     if (gx * gy > want) gx = (want + gy - 1) / gy;
     if (gx < 1) gx = 1;
     return dim3((unsigned)gx, (unsigned)gy);
   };
+  auto grid_for = [&](int64_t items) { return grid_for_warps(items, 8); };
   // forward: programs, then move the finished rows out; inverse: bring them in (scaled) first
   for (int step = 0; step < 2; ++step) {
     const bool rows_pass = inverse ? step == 0 : step == 1;
@@ -2234,9 +2243,9 @@ cudaError_t launch_p1_inplace(const P1Dev& P, double* xside, double* sside, int6
       if (P.nitems <= 0) continue;
       LaunchScope scope(kKindP1, stream);
       if (inverse)
-        p1_inplace_kernel<true><<<grid_for(P.nitems), 256, 0, stream>>>(P, xside, lgroups);
+        p1_inplace_kernel<true><<<grid_for_warps(P.nitems, p1_threads / 32), p1_threads, 0, stream>>>(P, xside, lgroups);
       else
-        p1_inplace_kernel<false><<<grid_for(P.nitems), 256, 0, stream>>>(P, xside, lgroups);
+        p1_inplace_kernel<false><<<grid_for_warps(P.nitems, p1_threads / 32), p1_threads, 0, stream>>>(P, xside, lgroups);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
