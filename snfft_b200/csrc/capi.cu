@@ -1458,6 +1458,19 @@ struct snfft_wreath {
   // the character sum at the irrep `parts`: it runs through the Clausen-Baum levels (forward_impl)
   snfft_plan* sn_plan = nullptr;
   int64_t sn_off = 0;
+  // Several cosets, a Young subgroup with a large factor and blocks too big for the fused kernel:
+  // stage 2 is the Fourier transform over S_a1 x S_a2 x S_a3 of h -> F_i(t_i h t_j^-1) at the irrep
+  // (parts_1, parts_2, parts_3), evaluated factor by factor with the S_a level recursion
+  // (forward_impl / inverse_impl of the factor's plan), last factor first.
+  struct Factor {
+    snfft_plan* plan;
+    int a;
+    int64_t fact, d, off;  // |S_a|, dimension and packed offset of the irrep parts_k
+  };
+  std::vector<Factor> ffts;  // the factors with a >= 2, in segment order
+  int seg_d[3] = {1, 1, 1};
+  bool factor_fft = false;
+  double *Y = nullptr, *Z = nullptr;  // with G: the three rotating buffers of the factor transforms
   double *sn_spec = nullptr, *sn_work = nullptr;
   double *R = nullptr, *RT = nullptr;                      // [nH][b*b] and its transpose
   double *Fre = nullptr, *Fim = nullptr, *G = nullptr, *P = nullptr;  // workspace
@@ -1601,6 +1614,8 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
       if (irrep < 0) throw InvalidArg("parts[" + std::to_string(k) + "] is not a partition of alpha[" + std::to_string(k) + "]");
       const int64_t d = shapes[irrep].dim, cnt = (int64_t)seg_perms[k].size();
       seg_dim[k] = (int)d;
+      w->seg_d[k] = (int)d;
+      if (a >= 2) w->ffts.push_back({fp, a, cnt, d, (int64_t)shapes[irrep].off});
       std::vector<int32_t> flat((size_t)cnt * a);
       for (int64_t r = 0; r < cnt; ++r)
         for (int q = 0; q < a; ++q) flat[r * a + q] = seg_perms[k][r][q];
@@ -1684,6 +1699,13 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
       w->sn_spec = w->alloc<double>((size_t)w->nfact);
       w->sn_work = w->alloc<double>((size_t)w->nfact);
     }
+    int a_max = 0;
+    for (const auto& f : w->ffts) a_max = std::max(a_max, f.a);
+    w->factor_fft = !w->sn_plan && !w->idx_t && a_max >= 4 && !std::getenv("SNFFT_WREATH_NO_FACTOR_FFT");
+    if (w->factor_fft) {
+      w->Y = w->alloc<double>((size_t)w->nfact * w->N);
+      w->Z = w->alloc<double>((size_t)w->nfact * w->N);
+    }
     CUDA_OK(cudaDeviceSynchronize());
   });
   if (rc != SNFFT_OK) {
@@ -1718,6 +1740,64 @@ int snfft_wreath_dims(const snfft_wreath* w, int64_t* dims) {
   });
 }
 
+// Stage 2 through the level recursion of the factors (see snfft_wreath::Factor).  Forward: one plane
+// of F -> one plane of the D x D matrix; inverse: one plane of the matrix -> one plane of F with
+// E[h] = <block, R[h]> (the inverse transforms return (d_k / a_k!) <rho_k, .> per factor: the
+// product of a_k! / d_k = |S_alpha| / b rides on the block regrouping).
+static void wreath_factor_forward(snfft_wreath* w, const double* F_plane, double* out_plane, cudaStream_t stream) {
+  const int64_t pairs = w->N * w->N;
+  double* bufs[3] = {w->G, w->Y, w->Z};
+  CUDA_OK(launch_gather(F_plane, w->idx, bufs[0], pairs * w->nH, 1, stream));  // [pair][h1][h2][h3]
+  int cur = 0;
+  int64_t outer = pairs * w->nH, inner = 1;
+  for (int q = (int)w->ffts.size() - 1; q >= 0; --q) {
+    const snfft_wreath::Factor& f = w->ffts[q];
+    outer /= f.fact;  // [outer][S_a][inner]
+    int in = cur;
+    if (inner > 1) {
+      in = (cur + 1) % 3;
+      CUDA_OK(launch_transpose_batched(bufs[cur], bufs[in], outer, f.fact, inner, stream));  // [outer][inner][S_a]
+    }
+    const int spec = (in + 1) % 3, work = (in + 2) % 3;
+    forward_impl(f.plan, f.a, bufs[in], bufs[spec], bufs[work], outer * inner, true, stream);
+    // the block of parts_k out of every packed spectrum: [outer][inner][d * d]
+    CUDA_OK(cudaMemcpy2DAsync(bufs[in], (size_t)(f.d * f.d) * sizeof(double), bufs[spec] + f.off,
+                              (size_t)f.fact * sizeof(double), (size_t)(f.d * f.d) * sizeof(double),
+                              (size_t)(outer * inner), cudaMemcpyDeviceToDevice, stream));
+    cur = in;
+    inner *= f.d * f.d;
+  }
+  CUDA_OK(launch_wreath_kron_permute(pairs, w->seg_d[0], w->seg_d[1], w->seg_d[2], bufs[cur], w->P, true, stream));
+  CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, out_plane, w->P, 1.0, true, stream));
+}
+
+static void wreath_factor_inverse(snfft_wreath* w, const double* mat_plane, double* F_plane, cudaStream_t stream) {
+  const int64_t pairs = w->N * w->N, bb = w->block * w->block;
+  double* bufs[3] = {w->G, w->Y, w->Z};
+  CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, const_cast<double*>(mat_plane), w->P,
+                                (double)w->nH / (double)w->block, false, stream));
+  CUDA_OK(launch_wreath_kron_permute(pairs, w->seg_d[0], w->seg_d[1], w->seg_d[2], bufs[0], w->P, false, stream));
+  int cur = 0;
+  int64_t outer = pairs, inner = bb;  // [pair][e3][e2][e1]
+  for (size_t q = 0; q < w->ffts.size(); ++q) {
+    const snfft_wreath::Factor& f = w->ffts[q];
+    inner /= f.d * f.d;  // [outer][inner][d * d]
+    const int spec = (cur + 1) % 3, fn = (cur + 2) % 3;
+    CUDA_OK(cudaMemsetAsync(bufs[spec], 0, (size_t)(outer * inner * f.fact) * sizeof(double), stream));
+    CUDA_OK(cudaMemcpy2DAsync(bufs[spec] + f.off, (size_t)f.fact * sizeof(double), bufs[cur],
+                              (size_t)(f.d * f.d) * sizeof(double), (size_t)(f.d * f.d) * sizeof(double),
+                              (size_t)(outer * inner), cudaMemcpyDeviceToDevice, stream));
+    inverse_impl(f.plan, f.a, bufs[spec], bufs[fn], bufs[cur], outer * inner, true, stream);  // [outer][inner][S_a]
+    if (inner > 1) {
+      CUDA_OK(launch_transpose_batched(bufs[fn], bufs[cur], outer, inner, f.fact, stream));  // [outer][S_a][inner]
+    } else {
+      cur = fn;
+    }
+    outer *= f.fact;
+  }
+  CUDA_OK(launch_gather(bufs[cur], w->inv_idx, F_plane, w->nfact * w->N, 1, stream));
+}
+
 int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_dev, double* out_im_dev, void* stream_) {
   return guarded([&] {
     if (!w || !f_dev || !out_re_dev || !out_im_dev) throw InvalidArg("null argument");
@@ -1746,6 +1826,11 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
                                    out_re_dev, out_im_dev, w->P, false, stream));
       return;
     }
+    if (w->factor_fft) {
+      wreath_factor_forward(w, w->Fre, out_re_dev, stream);
+      wreath_factor_forward(w, w->Fim, out_im_dev, stream);
+      return;
+    }
     for (int plane = 0; plane < 2; ++plane) {
       CUDA_OK(launch_gather(plane ? w->Fim : w->Fre, w->idx, w->G, pairs * w->nH, 1, stream));
       CUDA_OK(launch_dgemm(w->G, w->R, w->P, (int)pairs, (int)bb, (int)w->nH, stream));
@@ -1763,7 +1848,11 @@ int snfft_wreath_inverse(snfft_wreath* w, const double* fhat_re_dev, const doubl
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lock(w->mu);
     const int64_t bb = w->block * w->block, pairs = w->N * w->N;
-    for (int plane = 0; plane < 2 && !w->idx_t; ++plane) {
+    if (w->factor_fft) {
+      wreath_factor_inverse(w, fhat_re_dev, w->Fre, stream);
+      wreath_factor_inverse(w, fhat_im_dev, w->Fim, stream);
+    }
+    for (int plane = 0; plane < 2 && !w->idx_t && !w->factor_fft; ++plane) {
       CUDA_OK(launch_wreath_permute((int)w->N, (int)w->block, const_cast<double*>(plane ? fhat_im_dev : fhat_re_dev), w->P,
                                     1.0, false, stream));
       CUDA_OK(launch_dgemm(w->P, w->RT, w->G, (int)pairs, (int)w->nH, (int)bb, stream));  // [pairs][nH]

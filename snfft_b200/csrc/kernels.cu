@@ -1925,6 +1925,35 @@ __global__ void transpose_i64_kernel(const int64_t* __restrict__ in, int32_t* __
   }
 }
 
+// [batch][rows][cols] -> [batch][cols][rows]
+__global__ void transpose_batched_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t batch,
+                                         int64_t rows, int64_t cols) {
+  const int64_t per = rows * cols;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < batch * per; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = e / per, r = (e - bq * per) / cols, c = e - bq * per - r * cols;
+    out[bq * per + c * rows + r] = in[e];
+  }
+}
+
+// Blocks of a Young-subgroup irrep between the nesting the factor transforms leave,
+//   X[pair][e3][e2][e1], e_k = r_k d_k + c_k (entry of the factor-k matrix),
+// and the Kronecker order of R[h] = rho_1 (x) rho_2 (x) rho_3 (wreath.py:191-224),
+//   P[pair][((r1 d2 + r2) d3 + r3) b + (c1 d2 + c2) d3 + c3],  b = d1 d2 d3.
+template <bool TO_KRON>
+__global__ void wreath_kron_permute_kernel(int64_t pairs, int d1, int d2, int d3, double* __restrict__ X,
+                                           double* __restrict__ P) {
+  const int64_t b = (int64_t)d1 * d2 * d3, bb = b * b;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < pairs * bb; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = e / bb, q = e - p * bb;  // q indexes P
+    const int64_t row = q / b, col = q - row * b;
+    const int r3 = (int)(row % d3), r2 = (int)((row / d3) % d2), r1 = (int)(row / ((int64_t)d3 * d2));
+    const int c3 = (int)(col % d3), c2 = (int)((col / d3) % d2), c1 = (int)(col / ((int64_t)d3 * d2));
+    const int64_t e1 = r1 * d1 + c1, e2 = r2 * d2 + c2, e3 = r3 * d3 + c3;
+    const int64_t x = p * bb + (e3 * d2 * d2 + e2) * d1 * d1 + e1;
+    if (TO_KRON) P[e] = X[x]; else X[x] = P[e];
+  }
+}
+
 __global__ void transpose_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t rows, int64_t cols) {
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < rows * cols; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / cols, c = e - r * cols;
@@ -2366,6 +2395,25 @@ cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact,
   LaunchScope scope(kKindOther, stream);
   wreath_inverse_at_kernel<<<(unsigned)count, 256, 0, stream>>>(m, N, b, nH, nfact, n_ori, inv_idx, R, Mre, Mim, freq,
                                                                sigma, ori, scale, out_re, out_im);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose_batched(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                                     cudaStream_t stream) {
+  if (batch * rows * cols <= 0) return cudaSuccess;
+  LaunchScope scope(kKindOther, stream);
+  transpose_batched_kernel<<<grid_for(batch * rows * cols), 256, 0, stream>>>(in, out, batch, rows, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wreath_kron_permute(int64_t pairs, int d1, int d2, int d3, double* X, double* P, bool to_kron,
+                                       cudaStream_t stream) {
+  LaunchScope scope(kKindOther, stream);
+  const int64_t b = (int64_t)d1 * d2 * d3;
+  if (to_kron)
+    wreath_kron_permute_kernel<true><<<grid_for(pairs * b * b), 256, 0, stream>>>(pairs, d1, d2, d3, X, P);
+  else
+    wreath_kron_permute_kernel<false><<<grid_for(pairs * b * b), 256, 0, stream>>>(pairs, d1, d2, d3, X, P);
   return cudaGetLastError();
 }
 

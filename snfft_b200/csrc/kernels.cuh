@@ -81,6 +81,12 @@ cudaError_t launch_wreath_inverse_at(int m, int N, int b, int nH, int64_t nfact,
                                      const int64_t* sigma, const int32_t* ori, int64_t count, double scale,
                                      double* out_re, double* out_im, cudaStream_t stream);
 cudaError_t launch_transpose(const double* in, double* out, int64_t rows, int64_t cols, cudaStream_t stream);
+// [batch][rows][cols] -> [batch][cols][rows]
+cudaError_t launch_transpose_batched(const double* in, double* out, int64_t batch, int64_t rows, int64_t cols,
+                                     cudaStream_t stream);
+// X[pair][e3][e2][e1] (what the factor transforms leave) <-> P[pair][b*b] in the Kronecker order of R[h]
+cudaError_t launch_wreath_kron_permute(int64_t pairs, int d1, int d2, int d3, double* X, double* P, bool to_kron,
+                                       cudaStream_t stream);
 cudaError_t launch_transpose_i64(const int64_t* in, int32_t* out, int64_t rows, int64_t cols, cudaStream_t stream);  // narrows to 32 bits
 // stage 2 fused for small blocks (b*b in {1,4,9,16}, many cosets): gather + block sums + placement in one kernel
 bool wreath_stage2_fits(int N, int b, int nH);

@@ -270,7 +270,9 @@ class WreathPlan:
     Stage 1 (character sums over the orientations) is a radix-3 DFT over C_3^m in shared memory
     (``snfft_c3_dft``: one pass over f) whenever the orientation axis is the standard one
     (``orientation_mode``); an arbitrary orientation list falls back to the dense character GEMM.
-    Stage 2 (sum over the Young subgroup per coset pair) is one gather plus one DMMA GEMM."""
+    Stage 2 (sum over the Young subgroup per coset pair): behind the C plan a fused gather kernel for
+    small blocks, the S_a level recursion of the Young-subgroup factors when one has a >= 4, else one
+    gather plus one DMMA GEMM (also the path of this class's own fallback for general C_m)."""
 
     def __init__(self, alpha, parts, oris=None, device: int = 0):
         import torch

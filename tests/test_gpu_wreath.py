@@ -301,11 +301,40 @@ def test_c3_dft_building_block_against_numpy(m, count):
     assert torch.equal(both, torch.complex(ore, oim))
 
 
-def test_cube_inverse_small_blocks_against_sampled_inverse():
-    """The wreath inverse at a cube irrep with small blocks (N = 560 cosets, b = 2: F-major adjoint
-    of stage 2, interleaved F, complex128 output) against the sampled inverse, an independent
-    evaluation of d tr(rho(g)^H f_hat) / |G| that the oracle tests pin."""
-    alpha, parts = (2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))
+@pytest.mark.parametrize('alpha,parts', [((0, 4, 1), ((), (2, 2), (1,))), ((4, 0, 1), ((3, 1), (), (1,))),
+                                         ((1, 0, 4), ((1,), (), (2, 1, 1)))])
+def test_factor_recursion_against_oracle(alpha, parts):
+    """Stage 2 through the level recursion of the Young-subgroup factors (a factor S_4 here, several
+    cosets, blocks too large for the fused kernel): forward and inverse against the oracle's direct
+    evaluation on C3 wr S5."""
+    n = sum(alpha)
+    oris = W.orientations(n)
+    f = np.random.default_rng(700 + alpha[0]).standard_normal((math.factorial(n), len(oris)))
+    import snfft_b200 as sb
+    wp = WreathPlan(alpha, parts)
+    sb.timing_enable(True)
+    sb.timing_read()
+    got = wp.forward(torch.from_numpy(f).cuda()).cpu().numpy()
+    kinds = sb.timing_read()
+    sb.timing_enable(False)
+    # the S_4 factor really went through the level kernels (levels 2..4 fused), once per plane
+    assert kinds['fused_fwd'][1] == 2 and kinds['dgemm'][1] == 0
+    ref = W.wreath_ft_direct(alpha, parts, f, oris)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10
+    rng = np.random.default_rng(701)
+    fhat = rng.standard_normal((wp.D, wp.D)) + 1j * rng.standard_normal((wp.D, wp.D))
+    inv = wp.inverse(torch.from_numpy(fhat).cuda()).cpu().numpy()
+    want = W.wreath_inverse_direct(alpha, parts, fhat, oris, math.factorial(n) * len(oris))
+    assert np.abs(inv - want).max() < 1e-10 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize('alpha,parts', [((2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))),      # fused small blocks
+                                         ((0, 1, 7), ((), (1,), (4, 3))),             # one large factor, 8 cosets
+                                         ((0, 4, 4), ((), (2, 2), (3, 1)))])          # two factors S_4 x S_4
+def test_cube_inverse_against_sampled_inverse(alpha, parts):
+    """The wreath inverse at cube irreps (small blocks: F-major adjoint of stage 2, interleaved F;
+    large factors: the inverse level recursion factor by factor) against the sampled inverse, an
+    independent evaluation of d tr(rho(g)^H f_hat) / |G| that the oracle tests pin."""
     wp = WreathPlan(alpha, parts)
     f = torch.randn((40320, 2187), dtype=torch.float64, device='cuda',
                     generator=torch.Generator(device='cuda').manual_seed(91))
