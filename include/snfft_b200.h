@@ -247,8 +247,8 @@ int snfft_inverse_sharded(snfft_shard* shard, const double* fhat_compact_dev, do
  * f_dev: double[n!][orientations], sigma in perm2.sn order (lexicographic).  Output: the complex
  * D x D matrix as two row-major planes (D = cosets x block).  Stage 2 (the sums over the Young
  * subgroup per coset pair) runs as one fused gather kernel for small blocks, through the S_a level
- * recursion of the factors (the kernels of snfft_forward / snfft_inverse) when a factor has a >= 4,
- * and as gather + DMMA GEMM otherwise.  A plan serialises its transforms
+ * recursion of the Young-subgroup factors (the kernels of snfft_forward / snfft_inverse) otherwise;
+ * gather + DMMA GEMM only when every factor is trivial.  A plan serialises its transforms
  * (one shared workspace).  dims int64[6] = {D, cosets N, block, |S_alpha|, n!, orientations}. */
 typedef struct snfft_wreath snfft_wreath;
 int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int all_orientations, int device,

@@ -1458,7 +1458,7 @@ struct snfft_wreath {
   // the character sum at the irrep `parts`: it runs through the Clausen-Baum levels (forward_impl)
   snfft_plan* sn_plan = nullptr;
   int64_t sn_off = 0;
-  // Several cosets, a Young subgroup with a large factor and blocks too big for the fused kernel:
+  // Several cosets and blocks (or coset counts) outside the fused kernel's range:
   // stage 2 is the Fourier transform over S_a1 x S_a2 x S_a3 of h -> F_i(t_i h t_j^-1) at the irrep
   // (parts_1, parts_2, parts_3), evaluated factor by factor with the S_a level recursion
   // (forward_impl / inverse_impl of the factor's plan), last factor first.
@@ -1701,7 +1701,7 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     }
     int a_max = 0;
     for (const auto& f : w->ffts) a_max = std::max(a_max, f.a);
-    w->factor_fft = !w->sn_plan && !w->idx_t && a_max >= 4 && !std::getenv("SNFFT_WREATH_NO_FACTOR_FFT");
+    w->factor_fft = !w->sn_plan && !w->idx_t && a_max >= 2 && !std::getenv("SNFFT_WREATH_NO_FACTOR_FFT");
     if (w->factor_fft) {
       w->Y = w->alloc<double>((size_t)w->nfact * w->N);
       w->Z = w->alloc<double>((size_t)w->nfact * w->N);

@@ -271,8 +271,8 @@ class WreathPlan:
     (``snfft_c3_dft``: one pass over f) whenever the orientation axis is the standard one
     (``orientation_mode``); an arbitrary orientation list falls back to the dense character GEMM.
     Stage 2 (sum over the Young subgroup per coset pair): behind the C plan a fused gather kernel for
-    small blocks, the S_a level recursion of the Young-subgroup factors when one has a >= 4, else one
-    gather plus one DMMA GEMM (also the path of this class's own fallback for general C_m)."""
+    small blocks, else the S_a level recursion of the Young-subgroup factors; one gather plus one DMMA
+    GEMM in this class's own fallback for general C_m."""
 
     def __init__(self, alpha, parts, oris=None, device: int = 0):
         import torch
