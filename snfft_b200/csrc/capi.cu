@@ -1454,14 +1454,11 @@ struct snfft_wreath {
   int32_t* freq = nullptr;
   int64_t *idx = nullptr, *inv_idx = nullptr;
   int32_t* idx_t = nullptr;                                // idx transposed to [h][pair], 32-bit (fused stage 2), or null
-  // alpha = (n, 0, 0) up to order: S_alpha = S_n, one coset, and stage 2 IS the S_n Fourier transform of
-  // the character sum at the irrep `parts`: it runs through the Clausen-Baum levels (forward_impl)
-  snfft_plan* sn_plan = nullptr;
-  int64_t sn_off = 0;
-  // Several cosets and blocks (or coset counts) outside the fused kernel's range:
-  // stage 2 is the Fourier transform over S_a1 x S_a2 x S_a3 of h -> F_i(t_i h t_j^-1) at the irrep
-  // (parts_1, parts_2, parts_3), evaluated factor by factor with the S_a level recursion
-  // (forward_impl / inverse_impl of the factor's plan), last factor first.
+  // Outside the fused kernel's range (few cosets or large blocks): stage 2 is the Fourier transform
+  // over S_a1 x S_a2 x S_a3 of h -> F_i(t_i h t_j^-1) at the irrep (parts_1, parts_2, parts_3),
+  // evaluated factor by factor with the S_a level recursion (forward_impl / inverse_impl of the
+  // factor's plan), last factor first.  alpha = (n, 0, 0) up to order is the one-factor, one-coset
+  // instance: stage 2 IS the S_n Fourier transform of the character sum.
   struct Factor {
     snfft_plan* plan;
     int a;
@@ -1471,7 +1468,6 @@ struct snfft_wreath {
   int seg_d[3] = {1, 1, 1};
   bool factor_fft = false;
   double *Y = nullptr, *Z = nullptr;  // with G: the three rotating buffers of the factor transforms
-  double *sn_spec = nullptr, *sn_work = nullptr;
   double *R = nullptr, *RT = nullptr;                      // [nH][b*b] and its transpose
   double *Fre = nullptr, *Fim = nullptr, *G = nullptr, *P = nullptr;  // workspace
   std::vector<void*> allocs;
@@ -1625,10 +1621,6 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
       CUDA_OK(cudaDeviceSynchronize());
       if (nontrivial == 1) {
         single_dev = mats_dev;  // R is this factor's table itself
-        if (a == n && n >= 2) {
-          w->sn_plan = fp;
-          w->sn_off = shapes[irrep].off;
-        }
       } else {
         seg_mats[k].resize((size_t)cnt * d * d);
         CUDA_OK(cudaMemcpy(seg_mats[k].data(), mats_dev, seg_mats[k].size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1695,13 +1687,9 @@ int snfft_wreath_create(int n, const int32_t* alpha, const int32_t* parts, int a
     w->Fim = w->Fre + (size_t)w->nfact * w->N;
     w->G = w->alloc<double>((size_t)w->nfact * w->N);
     w->P = w->alloc<double>(2 * (size_t)w->N * w->N * bb);  // one plane of blocks (GEMM path) or complex blocks (fused adjoint)
-    if (w->sn_plan) {
-      w->sn_spec = w->alloc<double>((size_t)w->nfact);
-      w->sn_work = w->alloc<double>((size_t)w->nfact);
-    }
     int a_max = 0;
     for (const auto& f : w->ffts) a_max = std::max(a_max, f.a);
-    w->factor_fft = !w->sn_plan && !w->idx_t && a_max >= 2 && !std::getenv("SNFFT_WREATH_NO_FACTOR_FFT");
+    w->factor_fft = !w->idx_t && a_max >= 2 && !std::getenv("SNFFT_WREATH_NO_FACTOR_FFT");
     if (w->factor_fft) {
       w->Y = w->alloc<double>((size_t)w->nfact * w->N);
       w->Z = w->alloc<double>((size_t)w->nfact * w->N);
@@ -1806,21 +1794,12 @@ int snfft_wreath_forward(snfft_wreath* w, const double* f_dev, double* out_re_de
     std::lock_guard<std::mutex> lock(w->mu);
     const int64_t bb = w->block * w->block, pairs = w->N * w->N;
     // stage 1: character sums over the orientations, F_i(sigma) (one pass over f)
-    const bool fused = w->idx_t && !w->sn_plan;  // F interleaved (see snfft_wreath_create)
+    const bool fused = w->idx_t != nullptr;  // F interleaved (see snfft_wreath_create)
     CUDA_OK(launch_c3_dft(w->m, f_dev, nullptr, w->freq, (int)w->N, w->nfact, w->Fre, fused ? nullptr : w->Fim, false,
                           1.0, stream));
-    // stage 2: per coset pair the sum over the Young subgroup.  One coset (S_alpha = S_n): the S_n
-    // transform of F itself - the same level recursion as snfft_forward, from lexicographic order -
-    // and the block of the irrep `parts` out of the packed spectrum.  Small blocks: one fused kernel;
-    // otherwise gather by sigma = t_i h t_j^-1, one DMMA GEMM and the block placement per plane
-    if (w->sn_plan) {
-      for (int plane = 0; plane < 2; ++plane) {
-        forward_impl(w->sn_plan, w->n, plane ? w->Fim : w->Fre, w->sn_spec, w->sn_work, 1, true, stream);
-        CUDA_OK(cudaMemcpyAsync(plane ? out_im_dev : out_re_dev, w->sn_spec + w->sn_off, (size_t)bb * sizeof(double),
-                                cudaMemcpyDeviceToDevice, stream));
-      }
-      return;
-    }
+    // stage 2: per coset pair the sum over the Young subgroup.  Small blocks: one fused kernel;
+    // otherwise the level recursion of the Young-subgroup factors (one coset, S_alpha = S_n: the S_n
+    // transform of F itself); trivial subgroups: gather, one DMMA GEMM and the block placement
     if (fused) {
       CUDA_OK(launch_wreath_stage2((int)w->N, (int)w->block, (int)w->nH, w->nfact, w->idx_t, w->inv_idx, w->R, w->Fre,
                                    out_re_dev, out_im_dev, w->P, false, stream));

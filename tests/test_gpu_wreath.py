@@ -330,7 +330,8 @@ def test_factor_recursion_against_oracle(alpha, parts):
 
 @pytest.mark.parametrize('alpha,parts', [((2, 3, 3), ((1, 1), (1, 1, 1), (2, 1))),      # fused small blocks
                                          ((0, 1, 7), ((), (1,), (4, 3))),             # one large factor, 8 cosets
-                                         ((0, 4, 4), ((), (2, 2), (3, 1)))])          # two factors S_4 x S_4
+                                         ((0, 4, 4), ((), (2, 2), (3, 1))),           # two factors S_4 x S_4
+                                         ((8, 0, 0), ((6, 2), (), ()))])              # one coset: S_8 itself
 def test_cube_inverse_against_sampled_inverse(alpha, parts):
     """The wreath inverse at cube irreps (small blocks: F-major adjoint of stage 2, interleaved F;
     large factors: the inverse level recursion factor by factor) against the sampled inverse, an
