@@ -7,10 +7,14 @@ wreath.py:281-315) and D(o) the block-scalar matrix of cyclic characters (wreath
 :123-143).  The transform  f_hat = sum_g f(g) rho(g)  (multi.py:25-46, cube_ft.py:53-61) factors
 into (1) character sums over the orientations, F_i(sigma) = sum_o f(o, sigma) chi_i(o), and (2) for
 every coset pair a sum over the Young subgroup, block(i, j) = sum_h F_i(t_i h t_j^-1) rho_parts(h)
-(SURVEY.md 7.0(10)); both are dense fp64 products evaluated on the DMMA tensor pipe
-(``snfft_dgemm``), regrouped by one index gather (``snfft_gather``).  All arithmetic is complex128
-(the reference uses complex64 scalars).  ``WreathPlan`` needs a CUDA device; the dictionary-based
-helpers (``wreath_yor``, ``get_mat``, ``wreath_rep``) are host-side glue like the reference's.
+(SURVEY.md 7.0(10)).  For the standard C_3 orientation layouts the whole transform lives behind the
+C ABI (``snfft_wreath_create / _forward / _inverse / _inverse_at``): (1) is a DFT over C_3^m in
+shared memory, (2) a fused gather kernel for small blocks or the S_a level recursion of the
+Young-subgroup factors.  Other groups (C_2 wr S_n, arbitrary orientation lists) run the same two
+stages from this module as dense fp64 products on the DMMA tensor pipe (``snfft_dgemm``), regrouped
+by one index gather (``snfft_gather``).  All arithmetic is complex128 (the reference uses complex64
+scalars).  ``WreathPlan`` needs a CUDA device; the dictionary-based helpers (``wreath_yor``,
+``get_mat``, ``wreath_rep``) are host-side glue like the reference's.
 """
 from __future__ import annotations
 
