@@ -1379,8 +1379,14 @@ __device__ __forceinline__ void c3_digits(double2* __restrict__ g, int base, int
 
 // threads per CTA, measured for the cube (3^7 grid, 243 radix-9 tasks per pass): the forward kernel is
 // fastest with all tasks of a pass in one round (0.300 -> 0.267 ms), the adjoint with two rounds of 128
-// (0.488 vs 0.582 ms with 256)
-constexpr int kDftThreadsFwd = 256, kDftThreadsAdj = 128;
+// (adjoint: 0.582 / 0.560 / 0.487 / 0.550 / 0.560 / 0.582 ms with 64 / 96 / 128 / 160 / 192 / 256 threads)
+#ifndef SNFFT_C3_FWD_THREADS
+#define SNFFT_C3_FWD_THREADS 256
+#endif
+#ifndef SNFFT_C3_ADJ_THREADS
+#define SNFFT_C3_ADJ_THREADS 128
+#endif
+constexpr int kDftThreadsFwd = SNFFT_C3_FWD_THREADS, kDftThreadsAdj = SNFFT_C3_ADJ_THREADS;
 
 // Forward: the input rows are REAL, so one complex transform serves TWO rows: z = f(s1,.) + i f(s2,.),
 // Z = DFT(z), and F_1(k) = (Z(k) + conj Z(-k)) / 2, F_2(k) = (Z(k) - conj Z(-k)) / 2i.  One CTA =
