@@ -143,7 +143,7 @@ def bind_to_gpu_numa_node(local):
             return None
         os.sched_setaffinity(0, allowed)
         return node
-    except (OSError, ValueError, AttributeError):
+    except Exception:   # no GPU, no sysfs, no permission: placement is best effort
         return None
 
 
